@@ -1,0 +1,255 @@
+// Multi-head self-attention of the DINOv2 blocks (reference: dinov2/layers/attention.py:70-81, SDPA with
+// scale hd^-0.5, no mask) as one tcgen05 kernel: S = Q K^T and O~ = P V on the tensor cores with TMEM accumulators,
+// online softmax in registers, two 128-row query tiles per CTA ping-ponging on the tensor pipe.
+//
+// Layout: qkv is the QKV-GEMM output [B, N, 3*D] (16-bit); Q/K/V tiles of head h are the column windows
+// [h*64, D+h*64, 2D+h*64) fetched by TMA straight from that buffer (no head-major repack): Q and K tiles are
+// K-major UMMA operands, the V tile ([kv][hd], hd contiguous) is consumed as an MN-major B operand.
+// Output: out[b*N + q, h*64 + d] (16-bit), the A operand of the projection GEMM.
+#include "common.cuh"
+#include "host_api.h"
+
+namespace mg {
+
+constexpr int ATT_HD = 64;
+constexpr int ATT_BQ = 128;       // query rows per softmax warpgroup
+constexpr int ATT_BKV = 128;      // keys per tile
+constexpr int ATT_KV_STAGES = 3;
+constexpr int ATT_TILE_BYTES = 128 * 128;   // [128 rows][64 x 16-bit]
+constexpr int ATT_THREADS = 64 + 256;
+// smem: Q0,Q1 | K[3] | V[3] | P0 (2 atoms) | P1 (2 atoms) | barriers
+constexpr int ATT_SMEM = (2 + 2 * ATT_KV_STAGES + 4) * ATT_TILE_BYTES + 1024 + 256;
+
+struct AttnParams {
+    void* out;        // [B*N, D] 16-bit
+    int B, N, D, heads;
+    float scale_log2; // hd^-0.5 * log2(e)
+};
+
+template <bool BF16>
+__global__ void __launch_bounds__(ATT_THREADS, 1)
+attention_kernel(const __grid_constant__ CUtensorMap mapQKV, const AttnParams p) {
+    using H = H16<BF16>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint8_t* sQ = smem;                                        // 2 tiles
+    uint8_t* sK = sQ + 2 * ATT_TILE_BYTES;                     // 3 tiles
+    uint8_t* sV = sK + ATT_KV_STAGES * ATT_TILE_BYTES;         // 3 tiles
+    uint8_t* sP = sV + ATT_KV_STAGES * ATT_TILE_BYTES;         // 2 groups x 2 atoms
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 4 * ATT_TILE_BYTES);
+    uint64_t* q_full = bars;                 // 1
+    uint64_t* k_full = bars + 1;             // 3
+    uint64_t* k_empty = bars + 4;            // 3
+    uint64_t* v_full = bars + 7;             // 3
+    uint64_t* v_empty = bars + 10;           // 3
+    uint64_t* s_full = bars + 13;            // 2
+    uint64_t* p_full = bars + 15;            // 2
+    uint64_t* o_full = bars + 17;            // 2 groups x 2 buffers
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 21);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int q0 = blockIdx.x * 2 * ATT_BQ;
+    const int h = blockIdx.y, b = blockIdx.z;
+    const int nkv = (p.N + ATT_BKV - 1) / ATT_BKV;
+
+    if (threadIdx.x == 0) {
+        tma_prefetch_desc(&mapQKV);
+        mbar_init(q_full, 1);
+        for (int s = 0; s < ATT_KV_STAGES; ++s) {
+            mbar_init(&k_full[s], 1); mbar_init(&k_empty[s], 1);
+            mbar_init(&v_full[s], 1); mbar_init(&v_empty[s], 1);
+        }
+        for (int g = 0; g < 2; ++g) {
+            mbar_init(&s_full[g], 1); mbar_init(&p_full[g], 4);
+            mbar_init(&o_full[2 * g], 1); mbar_init(&o_full[2 * g + 1], 1);
+        }
+        fence_mbar_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+    // TMEM columns: S0 [0,128) S1 [128,256) O0 buffers [256,320),[320,384)  O1 buffers [384,448),[448,512)
+
+    if (warp == 0) {
+        if (lane == 0) {
+            mbar_arrive_expect_tx(q_full, 2 * ATT_TILE_BYTES);
+            tma_load_3d(sQ, &mapQKV, q_full, h * ATT_HD, q0, b);
+            tma_load_3d(sQ + ATT_TILE_BYTES, &mapQKV, q_full, h * ATT_HD, q0 + ATT_BQ, b);
+            for (int j = 0; j < nkv; ++j) {
+                const int s = j % ATT_KV_STAGES;
+                const uint32_t ph = (j / ATT_KV_STAGES) & 1;
+                mbar_wait(&k_empty[s], ph ^ 1);
+                mbar_arrive_expect_tx(&k_full[s], ATT_TILE_BYTES);
+                tma_load_3d(sK + s * ATT_TILE_BYTES, &mapQKV, &k_full[s], p.D + h * ATT_HD, j * ATT_BKV, b);
+                mbar_wait(&v_empty[s], ph ^ 1);
+                mbar_arrive_expect_tx(&v_full[s], ATT_TILE_BYTES);
+                tma_load_3d(sV + s * ATT_TILE_BYTES, &mapQKV, &v_full[s], 2 * p.D + h * ATT_HD, j * ATT_BKV, b);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc_s = make_idesc(128, ATT_BKV, BF16 ? 1u : 0u, 0, 0);   // Q (K-major) x K (K-major)
+            constexpr uint32_t idesc_o = make_idesc(128, ATT_HD, BF16 ? 1u : 0u, 0, 1);    // P (K-major) x V (MN-major)
+            auto issue_s = [&](int g, int j) {
+                const uint64_t a = make_sdesc_sw128(smem_u32(sQ + g * ATT_TILE_BYTES));
+                const uint64_t bd = make_sdesc_sw128(smem_u32(sK + (j % ATT_KV_STAGES) * ATT_TILE_BYTES));
+#pragma unroll
+                for (int k = 0; k < ATT_HD / 16; ++k) umma_f16(tmem + g * 128, a + 2 * k, bd + 2 * k, idesc_s, k != 0);
+                umma_commit(&s_full[g]);
+            };
+            auto issue_pv = [&](int g, int j) {
+                const uint32_t pa = smem_u32(sP + g * 2 * ATT_TILE_BYTES);
+                const uint32_t va = smem_u32(sV + (j % ATT_KV_STAGES) * ATT_TILE_BYTES);
+                const uint32_t d = tmem + 256 + g * 128 + (j & 1) * 64;
+#pragma unroll
+                for (int k = 0; k < ATT_BKV / 16; ++k) {
+                    // A: P, K-major; 4 K-steps per 64-column swizzle atom (atoms 16 KB apart)
+                    const uint64_t a = make_sdesc_sw128(pa + (k >> 2) * ATT_TILE_BYTES) + 2 * (k & 3);
+                    // B: V tile [kv][hd]: MN-major, 16 kv rows (= 2 groups of 8 x 128 B) per K-step
+                    const uint64_t bd = make_sdesc_sw128(va + k * 16 * 128, /*lbo=*/ATT_TILE_BYTES, /*sbo=*/1024);
+                    umma_f16(d, a, bd, idesc_o, k != 0);
+                }
+                umma_commit(&o_full[2 * g + (j & 1)]);
+            };
+            mbar_wait(q_full, 0);
+            mbar_wait(&k_full[0], 0);
+            tc_fence_after();
+            issue_s(0, 0);
+            issue_s(1, 0);
+            umma_commit(&k_empty[0]);
+            for (int j = 0; j < nkv; ++j) {
+                for (int g = 0; g < 2; ++g) {
+                    mbar_wait(&p_full[g], j & 1);
+                    tc_fence_after();
+                    if (j + 1 < nkv) {
+                        const int s1 = (j + 1) % ATT_KV_STAGES;
+                        if (g == 0) { mbar_wait(&k_full[s1], ((j + 1) / ATT_KV_STAGES) & 1); tc_fence_after(); }
+                        issue_s(g, j + 1);
+                        if (g == 1) umma_commit(&k_empty[s1]);
+                    }
+                    if (g == 0) { mbar_wait(&v_full[j % ATT_KV_STAGES], (j / ATT_KV_STAGES) & 1); tc_fence_after(); }
+                    issue_pv(g, j);
+                    if (g == 1) umma_commit(&v_empty[j % ATT_KV_STAGES]);
+                }
+            }
+        }
+    } else {
+        // ========================================================== softmax / accumulate / store (one row per thread)
+        const int g = (warp - 2) >> 2;
+        const int quarter = warp & 3;
+        const int row = quarter * 32 + lane;
+        const int qrow = q0 + g * ATT_BQ + row;
+        const uint32_t lane_sel = static_cast<uint32_t>(quarter * 32) << 16;
+        const uint32_t tS = tmem + lane_sel + g * 128;
+        const uint32_t tO = tmem + lane_sel + 256 + g * 128;
+        uint8_t* myP = sP + g * 2 * ATT_TILE_BYTES + (row >> 3) * 1024 + (row & 7) * 128;
+        const int sw = row & 7;
+        float o[ATT_HD];
+#pragma unroll
+        for (int i = 0; i < ATT_HD; ++i) o[i] = 0.f;
+        float m = -INFINITY, l = 0.f;
+        const float sc = p.scale_log2;
+        for (int j = 0; j < nkv; ++j) {
+            mbar_wait(&s_full[g], j & 1);
+            tc_fence_after();
+            const int kv_left = p.N - j * ATT_BKV;       // columns >= kv_left are padding
+            float mx = -INFINITY;
+#pragma unroll 1
+            for (int c = 0; c < ATT_BKV; c += 32) {
+                float v[32];
+                tmem_ld32(tS + c, v);
+                tc_wait_ld();
+#pragma unroll
+                for (int i = 0; i < 32; ++i) mx = fmaxf(mx, (c + i < kv_left) ? v[i] : -INFINITY);
+            }
+            const float m_new = fmaxf(m, mx);
+            const float alpha = exp2f((m - m_new) * sc);
+            if (j > 0) {
+                mbar_wait(&o_full[2 * g + ((j - 1) & 1)], ((j - 1) >> 1) & 1);
+                tc_fence_after();
+#pragma unroll
+                for (int c = 0; c < ATT_HD; c += 32) {
+                    float v[32];
+                    tmem_ld32(tO + ((j - 1) & 1) * 64 + c, v);
+                    tc_wait_ld();
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) o[c + i] = (o[c + i] + v[i]) * alpha;
+                }
+            }
+            l *= alpha;
+            const float mb = m_new * sc;
+#pragma unroll 1
+            for (int c = 0; c < ATT_BKV; c += 32) {
+                float v[32];
+                tmem_ld32(tS + c, v);
+                tc_wait_ld();
+                uint32_t w[16];
+#pragma unroll
+                for (int i = 0; i < 32; i += 2) {
+                    const float p0 = (c + i < kv_left) ? exp2f(v[i] * sc - mb) : 0.f;
+                    const float p1 = (c + i + 1 < kv_left) ? exp2f(v[i + 1] * sc - mb) : 0.f;
+                    l += p0 + p1;
+                    w[i >> 1] = H::pack(p0, p1);
+                }
+                uint8_t* atom = myP + (c >> 6) * ATT_TILE_BYTES;
+                const int chunk0 = (c & 63) >> 3;            // 16-byte chunk index of column c within the 128-byte row
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                    *reinterpret_cast<uint4*>(atom + (((chunk0 + q) ^ sw) << 4)) =
+                        make_uint4(w[4 * q], w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]);
+            }
+            m = m_new;
+            fence_proxy_async_smem();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&p_full[g]);
+        }
+        mbar_wait(&o_full[2 * g + ((nkv - 1) & 1)], ((nkv - 1) >> 1) & 1);
+        tc_fence_after();
+        const float inv = 1.0f / l;
+#pragma unroll
+        for (int c = 0; c < ATT_HD; c += 32) {
+            float v[32];
+            tmem_ld32(tO + ((nkv - 1) & 1) * 64 + c, v);
+            tc_wait_ld();
+            if (qrow < p.N) {
+                uint4 q[4];
+                uint32_t* qw = reinterpret_cast<uint32_t*>(q);
+#pragma unroll
+                for (int i = 0; i < 32; i += 2) qw[i >> 1] = H::pack((o[c + i] + v[i]) * inv, (o[c + i + 1] + v[i + 1]) * inv);
+                uint4* dst = reinterpret_cast<uint4*>(static_cast<typename H::T*>(p.out) +
+                                                      (static_cast<size_t>(b) * p.N + qrow) * p.D + h * ATT_HD + c);
+                dst[0] = q[0]; dst[1] = q[1]; dst[2] = q[2]; dst[3] = q[3];
+            }
+            __syncwarp();
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem, 512);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ host
+int launch_attention(const CUtensorMap& mapQKV, void* out, int B, int N, int D, int heads, bool bf16, cudaStream_t st) {
+    if (D != heads * ATT_HD) return set_error("attention: head dim must be 64 (D=%d heads=%d)", D, heads);
+    AttnParams p;
+    p.out = out; p.B = B; p.N = N; p.D = D; p.heads = heads;
+    p.scale_log2 = 0.125f * 1.4426950408889634f;
+    dim3 grid((N + 2 * ATT_BQ - 1) / (2 * ATT_BQ), heads, B);
+    auto kern = bf16 ? attention_kernel<true> : attention_kernel<false>;
+    static bool attr_set[2] = {false, false};
+    if (!attr_set[bf16]) {
+        CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
+        attr_set[bf16] = true;
+    }
+    kern<<<grid, ATT_THREADS, ATT_SMEM, st>>>(mapQKV, p);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace mg

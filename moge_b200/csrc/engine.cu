@@ -1,0 +1,836 @@
+// Host runtime of libmoge_b200.so: weight registry + load-time repacking, per-shape execution plans (workspace
+// layout, TMA descriptors, launch list), and the extern "C" ABI declared in include/moge_b200.h.
+#include "moge_b200.h"
+#include "umma_kernel.cuh"
+#include "host_api.h"
+
+#include <algorithm>
+#include <functional>
+#include <map>
+#include <memory>
+#include <string>
+#include <vector>
+#include <math.h>
+
+namespace mg {
+
+const char* last_error();
+
+// ------------------------------------------------------------------------------------------------ helpers
+__global__ void to_f32_kernel(const void* src, int dtype, float* dst, size_t n) {
+    for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n; i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        if (dtype == MOGE_F32) dst[i] = static_cast<const float*>(src)[i];
+        else if (dtype == MOGE_F16) dst[i] = __half2float(static_cast<const __half*>(src)[i]);
+        else dst[i] = __bfloat162float(static_cast<const __nv_bfloat16*>(src)[i]);
+    }
+}
+// dst[i] = a[i*lda] + (b ? b[i] : 0)
+__global__ void vec_combine_kernel(float* dst, const float* a, int lda, const float* b, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = a[static_cast<size_t>(i) * lda] + (b ? b[i] : 0.f);
+}
+
+struct RawWeight {
+    float* p = nullptr;
+    std::vector<int64_t> shape;
+    size_t numel = 0;
+};
+
+struct Level { int H, W, Hp, Wp; };
+
+struct ConvW {          // packed 3x3 / 1x1 / convT weights for one launch
+    void* w = nullptr;  // [N, Ktot] 16-bit
+    float* bias = nullptr;
+    float* wu = nullptr;
+    float* wv = nullptr;
+    int N = 0, Ktot = 0, cin = 0, caux = 0, taps = 0;
+};
+
+struct StackW {
+    ConvW in0;                                  // heads: 1x1 input block at level 0
+    std::vector<std::vector<ConvW>> res;        // [level][2*r + {0,1}]
+    std::vector<ConvW> convT;                   // [level] (conv_transpose resampler)
+    std::vector<ConvW> post;                    // [level] 3x3 after the resampler (writes level l+1), fused in-block / UV
+    // folded last level of a head
+    ConvW headout;
+    float* waux = nullptr;
+    int ncomp = 0;
+};
+
+struct Plan {
+    int B, H, W, h, w;
+    void* ws;
+    size_t ws_bytes;
+    std::vector<std::function<int(cudaStream_t)>> ops;
+    float* pos_table = nullptr;   // engine-owned, [T, D]
+    float* cls_row = nullptr;
+    bool table_ready = false;
+    // output bindings (set per forward)
+    float* points = nullptr; float* normal = nullptr; float* mask = nullptr; float* scale = nullptr;
+    const void* image = nullptr; int image_dtype = 0;
+};
+
+}  // namespace mg
+
+using namespace mg;
+
+struct moge_engine {
+    moge_config_t cfg;
+    int device = 0, num_sms = 148;
+    bool bf16 = false, finalized = false;
+    std::map<std::string, RawWeight> raw;
+    std::vector<void*> owned;         // cudaMalloc'd, freed at destroy
+    // packed encoder
+    void* w_patch = nullptr;
+    struct Blk { void *wqkv, *wproj, *wfc1, *wfc2; const float *bqkv, *bproj, *bfc1, *bfc2, *g1, *g2, *ln1g, *ln1b, *ln2g, *ln2b; };
+    std::vector<Blk> blk;
+    const float *norm_g = nullptr, *norm_b = nullptr, *pos_embed = nullptr, *cls_token = nullptr, *patch_bias = nullptr;
+    ConvW fold0;                      // taps-concat GEMM: (output projections folded into neck.input_blocks.0)
+    StackW neck, heads[3];            // heads: points, normal, mask
+    std::vector<const float*> mlp_w, mlp_b;
+    std::vector<std::unique_ptr<Plan>> plans;
+
+    int alloc(void** p, size_t bytes) {
+        CUDA_TRY(cudaMalloc(p, bytes ? bytes : 16));
+        owned.push_back(*p);
+        return 0;
+    }
+};
+
+namespace mg {
+
+static const moge_stack_config_t* head_cfg(const moge_engine* e, int i) {
+    return i == 0 ? &e->cfg.points_head : i == 1 ? &e->cfg.normal_head : &e->cfg.mask_head;
+}
+static const char* head_name(int i) { return i == 0 ? "points_head" : i == 1 ? "normal_head" : "mask_head"; }
+
+static int get_raw(moge_engine* e, const std::string& key, const RawWeight** out, std::initializer_list<int64_t> shape) {
+    auto it = e->raw.find(key);
+    if (it == e->raw.end()) return set_error("missing weight '%s'", key.c_str());
+    if (shape.size()) {
+        if (it->second.shape.size() != shape.size() || !std::equal(shape.begin(), shape.end(), it->second.shape.begin())) {
+            std::string got;
+            for (auto d : it->second.shape) got += std::to_string(d) + ",";
+            std::string want;
+            for (auto d : shape) want += std::to_string(d) + ",";
+            return set_error("weight '%s' has shape (%s) expected (%s)", key.c_str(), got.c_str(), want.c_str());
+        }
+    }
+    *out = &it->second;
+    return 0;
+}
+
+static int pick_bn(int N, std::initializer_list<int> cands) {
+    for (int c : cands) if (N % c == 0) return c;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ finalize
+static int pack_linear(moge_engine* e, const std::string& key, int N, int K, int Kpad, void** out, cudaStream_t st) {
+    const RawWeight* w;
+    MG_TRY(get_raw(e, key, &w, {}));
+    if (static_cast<int64_t>(w->numel) != static_cast<int64_t>(N) * K) return set_error("weight '%s': numel %zu != %d*%d", key.c_str(), w->numel, N, K);
+    MG_TRY(e->alloc(out, static_cast<size_t>(N) * Kpad * 2));
+    return launch_cast_2d(w->p, MOGE_F32, *out, e->bf16, N, K, K, Kpad, st);
+}
+static int vec(moge_engine* e, const std::string& key, int n, const float** out) {
+    const RawWeight* w;
+    MG_TRY(get_raw(e, key, &w, {}));
+    if (static_cast<int>(w->numel) != n) return set_error("weight '%s': numel %zu != %d", key.c_str(), w->numel, n);
+    *out = w->p;
+    return 0;
+}
+// bias = a + b (b optional), engine-owned
+static int sum_bias(moge_engine* e, const float* a, const float* b, int n, float** out, cudaStream_t st) {
+    MG_TRY(e->alloc(reinterpret_cast<void**>(out), static_cast<size_t>(n) * 4));
+    vec_combine_kernel<<<(n + 255) / 256, 256, 0, st>>>(*out, a, 1, b, n);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+// 3x3 conv (Cout,Cin,3,3) [+ aux 1x1 (Cout,Caux,1,1)] [+ UV 1x1 (Cout,2,1,1)] -> ConvW
+static int pack_conv3(moge_engine* e, const std::string& wkey, int Cout, int Cin, const std::string& in_key, int Caux,
+                      bool uv, ConvW* cw, cudaStream_t st) {
+    const RawWeight* w;
+    MG_TRY(get_raw(e, wkey + ".weight", &w, {Cout, Cin, 3, 3}));
+    const float* b;
+    MG_TRY(vec(e, wkey + ".bias", Cout, &b));
+    if (Cin % 64) return set_error("conv '%s': C_in=%d must be a multiple of 64", wkey.c_str(), Cin);
+    cw->N = Cout; cw->cin = Cin; cw->caux = Caux; cw->taps = 9;
+    cw->Ktot = 9 * Cin + Caux;
+    MG_TRY(e->alloc(&cw->w, static_cast<size_t>(Cout) * cw->Ktot * 2));
+    MG_TRY(launch_pack_conv(w->p, cw->w, e->bf16, Cout, Cin, 9, cw->Ktot, 0, st));
+    const float* b_in = nullptr;
+    if (!in_key.empty()) {
+        const RawWeight* wi;
+        if (uv) {
+            MG_TRY(get_raw(e, in_key + ".weight", &wi, {Cout, 2, 1, 1}));
+            MG_TRY(e->alloc(reinterpret_cast<void**>(&cw->wu), Cout * 4));
+            MG_TRY(e->alloc(reinterpret_cast<void**>(&cw->wv), Cout * 4));
+            vec_combine_kernel<<<(Cout + 255) / 256, 256, 0, st>>>(cw->wu, wi->p, 2, nullptr, Cout);
+            vec_combine_kernel<<<(Cout + 255) / 256, 256, 0, st>>>(cw->wv, wi->p + 1, 2, nullptr, Cout);
+        } else {
+            if (Caux % 64) return set_error("input block '%s': C=%d must be a multiple of 64", in_key.c_str(), Caux);
+            MG_TRY(get_raw(e, in_key + ".weight", &wi, {Cout, Caux, 1, 1}));
+            MG_TRY(launch_pack_conv(wi->p, cw->w, e->bf16, Cout, Caux, 1, cw->Ktot, 9 * Cin, st));
+        }
+        MG_TRY(vec(e, in_key + ".bias", Cout, &b_in));
+    }
+    return sum_bias(e, b, b_in, Cout, &cw->bias, st);
+}
+
+static int pack_stack(moge_engine* e, const std::string& name, const moge_stack_config_t& sc, bool is_neck, StackW* sw,
+                      cudaStream_t st) {
+    const int L = sc.num_levels;
+    sw->res.assign(L, {});
+    sw->convT.assign(L, ConvW());
+    sw->post.assign(L, ConvW());
+    const int* C = sc.dim_res_blocks;
+    if (!is_neck) {
+        // level-0 input block: 1x1 conv C0 -> C0 on the neck's level-0 output
+        if (sc.dim_in[0] <= 0) return set_error("%s: level-0 input block required", name.c_str());
+        const RawWeight* w;
+        MG_TRY(get_raw(e, name + ".input_blocks.0.weight", &w, {C[0], sc.dim_in[0], 1, 1}));
+        if (sc.dim_in[0] % 64) return set_error("%s: level-0 C_in=%d must be a multiple of 64", name.c_str(), sc.dim_in[0]);
+        ConvW& cw = sw->in0;
+        cw.N = C[0]; cw.cin = sc.dim_in[0]; cw.taps = 1; cw.Ktot = sc.dim_in[0];
+        MG_TRY(e->alloc(&cw.w, static_cast<size_t>(cw.N) * cw.Ktot * 2));
+        MG_TRY(launch_pack_conv(w->p, cw.w, e->bf16, cw.N, cw.cin, 1, cw.Ktot, 0, st));
+        const float* b;
+        MG_TRY(vec(e, name + ".input_blocks.0.bias", C[0], &b));
+        MG_TRY(sum_bias(e, b, nullptr, C[0], &cw.bias, st));
+    }
+    for (int l = 0; l < L; ++l) {
+        const bool last = (l == L - 1);
+        if (sc.dim_out[l] > 0 && !(last && !is_neck)) return set_error("%s: output block at level %d unsupported", name.c_str(), l);
+        for (int r = 0; r < sc.num_res_blocks[l]; ++r) {
+            if (last && !is_neck) return set_error("%s: residual blocks at the last head level unsupported", name.c_str());
+            for (int k : {2, 5}) {
+                ConvW cw;
+                MG_TRY(pack_conv3(e, name + ".res_blocks." + std::to_string(l) + "." + std::to_string(r) + ".layers." + std::to_string(k),
+                                  C[l], C[l], "", 0, false, &cw, st));
+                sw->res[l].push_back(cw);
+            }
+        }
+        if (last) break;
+        const std::string rs = name + ".resamplers." + std::to_string(l);
+        const std::string in_key = sc.dim_in[l + 1] > 0 ? name + ".input_blocks." + std::to_string(l + 1) : std::string();
+        const bool fold_head_out = !is_neck && (l + 1 == L - 1);
+        int conv_cin;
+        if (sc.resamplers[l] == MOGE_RESAMPLE_CONV_TRANSPOSE) {
+            const RawWeight* w;
+            MG_TRY(get_raw(e, rs + ".0.weight", &w, {C[l], C[l + 1], 2, 2}));
+            if (C[l] % 64 || C[l + 1] % 32) return set_error("%s: convT %d->%d channel counts unsupported", name.c_str(), C[l], C[l + 1]);
+            ConvW& ct = sw->convT[l];
+            ct.N = 4 * C[l + 1]; ct.cin = C[l]; ct.taps = 1; ct.Ktot = C[l];
+            MG_TRY(e->alloc(&ct.w, static_cast<size_t>(ct.N) * ct.Ktot * 2));
+            MG_TRY(launch_pack_convT(w->p, ct.w, e->bf16, C[l], C[l + 1], st));
+            const float* b;
+            MG_TRY(vec(e, rs + ".0.bias", C[l + 1], &b));
+            MG_TRY(sum_bias(e, b, nullptr, C[l + 1], &ct.bias, st));
+            conv_cin = C[l + 1];
+        } else if (sc.resamplers[l] == MOGE_RESAMPLE_BILINEAR) {
+            conv_cin = C[l];
+        } else {
+            return set_error("%s: resampler type %d unsupported", name.c_str(), sc.resamplers[l]);
+        }
+        if (!fold_head_out) {
+            if (is_neck) {
+                if (sc.dim_in[l + 1] != 2) return set_error("neck: dim_in[%d] must be 2 (UV planes)", l + 1);
+                MG_TRY(pack_conv3(e, rs + ".1", C[l + 1], conv_cin, in_key, 0, true, &sw->post[l], st));
+            } else {
+                if (sc.dim_in[l + 1] <= 0) return set_error("%s: input block at level %d required", name.c_str(), l + 1);
+                MG_TRY(pack_conv3(e, rs + ".1", C[l + 1], conv_cin, in_key, sc.dim_in[l + 1], false, &sw->post[l], st));
+            }
+        } else {
+            // head tail: conv3x3 (conv_cin -> 32) + in_block(neck_last 32 -> 32) then output block 32 -> ncomp, no
+            // nonlinearity in between  =>  one 3x3 conv conv_cin -> ncomp plus a [ncomp,32] map of the neck map.
+            const int Cl = C[L - 1], nc = sc.dim_out[L - 1];
+            if (Cl != 32 || sc.dim_in[L - 1] != 32 || nc <= 0 || nc > 3 || conv_cin % 64)
+                return set_error("%s: last level must be 32 channels with a 1..3 channel output block", name.c_str());
+            const RawWeight *wc, *w4, *wo;
+            const float *bc, *b4, *bo;
+            MG_TRY(get_raw(e, rs + ".1.weight", &wc, {Cl, conv_cin, 3, 3}));
+            MG_TRY(vec(e, rs + ".1.bias", Cl, &bc));
+            MG_TRY(get_raw(e, in_key + ".weight", &w4, {Cl, 32, 1, 1}));
+            MG_TRY(vec(e, in_key + ".bias", Cl, &b4));
+            MG_TRY(get_raw(e, name + ".output_blocks." + std::to_string(L - 1) + ".weight", &wo, {nc, Cl, 1, 1}));
+            MG_TRY(vec(e, name + ".output_blocks." + std::to_string(L - 1) + ".bias", nc, &bo));
+            float *tmpw, *bsum, *bfold;
+            const int K9 = conv_cin * 9;
+            MG_TRY(e->alloc(reinterpret_cast<void**>(&tmpw), static_cast<size_t>(16) * K9 * 4));
+            CUDA_TRY(cudaMemsetAsync(tmpw, 0, static_cast<size_t>(16) * K9 * 4, st));
+            MG_TRY(launch_sgemm(wo->p, Cl, wc->p, K9, tmpw, K9, nc, K9, Cl, 0, st));          // [nc, (ci,tap)]
+            ConvW& ho = sw->headout;
+            ho.N = 16; ho.cin = conv_cin; ho.taps = 9; ho.Ktot = K9;
+            MG_TRY(e->alloc(&ho.w, static_cast<size_t>(16) * K9 * 2));
+            MG_TRY(launch_pack_conv(tmpw, ho.w, e->bf16, 16, conv_cin, 9, K9, 0, st));
+            MG_TRY(e->alloc(reinterpret_cast<void**>(&sw->waux), 3 * 32 * 4));
+            CUDA_TRY(cudaMemsetAsync(sw->waux, 0, 3 * 32 * 4, st));
+            MG_TRY(launch_sgemm(wo->p, Cl, w4->p, 32, sw->waux, 32, nc, 32, Cl, 0, st));       // [nc, 32]
+            MG_TRY(sum_bias(e, bc, b4, Cl, &bsum, st));
+            MG_TRY(e->alloc(reinterpret_cast<void**>(&bfold), 16 * 4));
+            CUDA_TRY(cudaMemsetAsync(bfold, 0, 16 * 4, st));
+            MG_TRY(launch_sgemm(wo->p, Cl, bsum, 1, bfold, 1, nc, 1, Cl, 0, st));
+            vec_combine_kernel<<<1, 32, 0, st>>>(bfold, bfold, 1, bo, nc);
+            CUDA_TRY(cudaGetLastError());
+            ho.bias = bfold;
+            sw->ncomp = nc;
+        }
+    }
+    return 0;
+}
+
+static int finalize(moge_engine* e, cudaStream_t st) {
+    const moge_config_t& c = e->cfg;
+    const int D = c.embed_dim;
+    const std::string bb = "encoder.backbone.";
+    MG_TRY(pack_linear(e, bb + "patch_embed.proj.weight", D, 588, 592, &e->w_patch, st));
+    MG_TRY(vec(e, bb + "patch_embed.proj.bias", D, &e->patch_bias));
+    MG_TRY(vec(e, bb + "pos_embed", (1 + 37 * 37) * D, &e->pos_embed));
+    MG_TRY(vec(e, bb + "cls_token", D, &e->cls_token));
+    MG_TRY(vec(e, bb + "norm.weight", D, &e->norm_g));
+    MG_TRY(vec(e, bb + "norm.bias", D, &e->norm_b));
+    e->blk.resize(c.depth);
+    for (int i = 0; i < c.depth; ++i) {
+        const std::string p = bb + "blocks." + std::to_string(i) + ".";
+        moge_engine::Blk& b = e->blk[i];
+        MG_TRY(pack_linear(e, p + "attn.qkv.weight", 3 * D, D, D, &b.wqkv, st));
+        MG_TRY(pack_linear(e, p + "attn.proj.weight", D, D, D, &b.wproj, st));
+        MG_TRY(pack_linear(e, p + "mlp.fc1.weight", 4 * D, D, D, &b.wfc1, st));
+        MG_TRY(pack_linear(e, p + "mlp.fc2.weight", D, 4 * D, 4 * D, &b.wfc2, st));
+        MG_TRY(vec(e, p + "attn.qkv.bias", 3 * D, &b.bqkv));
+        MG_TRY(vec(e, p + "attn.proj.bias", D, &b.bproj));
+        MG_TRY(vec(e, p + "mlp.fc1.bias", 4 * D, &b.bfc1));
+        MG_TRY(vec(e, p + "mlp.fc2.bias", D, &b.bfc2));
+        MG_TRY(vec(e, p + "ls1.gamma", D, &b.g1));
+        MG_TRY(vec(e, p + "ls2.gamma", D, &b.g2));
+        MG_TRY(vec(e, p + "norm1.weight", D, &b.ln1g));
+        MG_TRY(vec(e, p + "norm1.bias", D, &b.ln1b));
+        MG_TRY(vec(e, p + "norm2.weight", D, &b.ln2g));
+        MG_TRY(vec(e, p + "norm2.bias", D, &b.ln2b));
+    }
+    // ---- fold: neck.input_blocks.0 o (sum_j output_projections.j)  ->  one GEMM over the concatenated taps
+    {
+        const int C0 = c.neck.dim_res_blocks[0], Do = c.dim_out, nt = c.num_taps;
+        if (c.neck.dim_in[0] != Do + 2) return set_error("neck.dim_in[0]=%d must be encoder.dim_out+2=%d", c.neck.dim_in[0], Do + 2);
+        const RawWeight* w0;
+        MG_TRY(get_raw(e, "neck.input_blocks.0.weight", &w0, {C0, Do + 2, 1, 1}));
+        const float* b0;
+        MG_TRY(vec(e, "neck.input_blocks.0.bias", C0, &b0));
+        float *wf, *bf, *bp;
+        MG_TRY(e->alloc(reinterpret_cast<void**>(&wf), static_cast<size_t>(C0) * nt * D * 4));
+        MG_TRY(e->alloc(reinterpret_cast<void**>(&bf), C0 * 4));
+        MG_TRY(e->alloc(reinterpret_cast<void**>(&bp), Do * 4));
+        CUDA_TRY(cudaMemsetAsync(bp, 0, Do * 4, st));
+        for (int j = 0; j < nt; ++j) {
+            const RawWeight* pj;
+            MG_TRY(get_raw(e, "encoder.output_projections." + std::to_string(j) + ".weight", &pj, {Do, D, 1, 1}));
+            const float* bj;
+            MG_TRY(vec(e, "encoder.output_projections." + std::to_string(j) + ".bias", Do, &bj));
+            MG_TRY(launch_sgemm(w0->p, Do + 2, pj->p, D, wf + static_cast<size_t>(j) * D, nt * D, C0, D, Do, 0, st));
+            vec_combine_kernel<<<(Do + 255) / 256, 256, 0, st>>>(bp, bp, 1, bj, Do);
+        }
+        MG_TRY(launch_sgemm(w0->p, Do + 2, bp, 1, bf, 1, C0, 1, Do, 0, st));
+        vec_combine_kernel<<<(C0 + 255) / 256, 256, 0, st>>>(bf, bf, 1, b0, C0);
+        ConvW& f = e->fold0;
+        f.N = C0; f.Ktot = nt * D; f.taps = 1; f.cin = nt * D;
+        MG_TRY(e->alloc(&f.w, static_cast<size_t>(C0) * f.Ktot * 2));
+        MG_TRY(launch_cast_2d(wf, MOGE_F32, f.w, e->bf16, C0, f.Ktot, f.Ktot, f.Ktot, st));
+        f.bias = bf;
+        MG_TRY(e->alloc(reinterpret_cast<void**>(&f.wu), C0 * 4));
+        MG_TRY(e->alloc(reinterpret_cast<void**>(&f.wv), C0 * 4));
+        vec_combine_kernel<<<(C0 + 255) / 256, 256, 0, st>>>(f.wu, w0->p + Do, Do + 2, nullptr, C0);
+        vec_combine_kernel<<<(C0 + 255) / 256, 256, 0, st>>>(f.wv, w0->p + Do + 1, Do + 2, nullptr, C0);
+        CUDA_TRY(cudaGetLastError());
+    }
+    MG_TRY(pack_stack(e, "neck", c.neck, true, &e->neck, st));
+    for (int i = 0; i < 3; ++i)
+        if (head_cfg(e, i)->present) MG_TRY(pack_stack(e, head_name(i), *head_cfg(e, i), false, &e->heads[i], st));
+    for (int l = 0; l < c.scale_head_layers; ++l) {
+        const float *w, *b;
+        MG_TRY(vec(e, "scale_head." + std::to_string(2 * l) + ".weight", c.scale_head_dims[l] * c.scale_head_dims[l + 1], &w));
+        MG_TRY(vec(e, "scale_head." + std::to_string(2 * l) + ".bias", c.scale_head_dims[l + 1], &b));
+        e->mlp_w.push_back(w);
+        e->mlp_b.push_back(b);
+    }
+    CUDA_TRY(cudaStreamSynchronize(st));
+    // release the fp32 staging copies of the big matrices (vectors stay: kernels read them directly)
+    for (auto& kv : e->raw) {
+        const bool keep = kv.second.shape.size() <= 1 || kv.first.find("pos_embed") != std::string::npos ||
+                          kv.first.find("cls_token") != std::string::npos || kv.first.rfind("scale_head.", 0) == 0;
+        if (!keep && kv.second.p) { cudaFree(kv.second.p); kv.second.p = nullptr; }
+    }
+    e->finalized = true;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ planning
+struct WsAlloc {
+    uint8_t* base; size_t off = 0;
+    explicit WsAlloc(void* b) : base(static_cast<uint8_t*>(b)) {}
+    void* take(size_t bytes) {
+        off = (off + 1023) & ~static_cast<size_t>(1023);
+        void* p = base ? base + off : nullptr;
+        off += bytes;
+        return p;
+    }
+};
+
+static Level level_geom(int h, int w, int l) {
+    Level g;
+    g.H = h << l; g.W = w << l;
+    g.Hp = std::max(g.H + 2, TILE_PH);
+    g.Wp = std::max(g.W + 2, TILE_PW);
+    return g;
+}
+static size_t map_bytes(const Level& g, int B, int C) { return static_cast<size_t>(B) * g.Hp * g.Wp * C * 2; }
+
+// conv-type launch on padded NHWC maps. src/aux/skip/out buffers live in the workspace.
+static int add_conv(moge_engine* e, Plan* pl, const ConvW& cw, const void* src, const void* aux, const Level& gs, int B,
+                    int epi, void* out_raw, void* out_relu, const void* skip, const Level& go, int out_ch, bool shuffle,
+                    bool uv, float su, float sv, int ncomp = 0, const float* waux = nullptr) {
+    UmmaParams p{};
+    p.N = cw.N; p.ntaps = cw.taps; p.kb_main = cw.cin / 64; p.kb_aux = cw.caux / 64;
+    p.B = B; p.H = gs.H; p.W = gs.W;
+    p.tiles_x = (gs.W + TILE_PW - 1) / TILE_PW; p.tiles_y = (gs.H + TILE_PH - 1) / TILE_PH;
+    p.num_m_tiles = B * p.tiles_x * p.tiles_y;
+    int bn;
+    if (epi == EPI_HEADOUT) bn = 16;
+    else bn = pick_bn(cw.N, {256, 128, 64, 32});
+    if (!bn) return set_error("conv: N=%d has no tile width", cw.N);
+    p.num_n_tiles = cw.N / bn;
+    p.out0 = out_raw; p.out1 = out_relu; p.bias = cw.bias;
+    p.vec1 = uv ? cw.wu : nullptr; p.vec2 = uv ? cw.wv : nullptr;
+    p.skip = skip; p.ldo = out_ch;
+    p.Ho = go.H; p.Wo = go.W; p.Hop = go.Hp; p.Wop = go.Wp;
+    p.shuffle = shuffle ? 1 : 0; p.su = su; p.sv = sv;
+    if (epi == EPI_HEADOUT) { p.vec1 = waux; p.ncomp = ncomp; }
+    CUtensorMap ma, mx, mb;
+    MG_TRY(make_map_nhwc(&ma, src, cw.cin, gs.Wp, gs.Hp, B));
+    if (cw.caux) MG_TRY(make_map_nhwc(&mx, aux, cw.caux, gs.Wp, gs.Hp, B));
+    else mx = ma;
+    MG_TRY(make_map_2d(&mb, cw.w, cw.Ktot, cw.N, cw.Ktot, bn));
+    const bool bf16 = e->bf16; const int sms = e->num_sms;
+    pl->ops.push_back([=](cudaStream_t st) { return launch_umma(bn, AMODE_TILES, epi, bf16, ma, mx, mb, p, sms, st); });
+    return 0;
+}
+
+static int add_linear(moge_engine* e, Plan* pl, const void* A, int M, int K, int lda, const void* W, int N, int epi,
+                      void* out, const float* bias, const float* v1, int ldo, int T = 0, int gridw = 0) {
+    UmmaParams p{};
+    p.M = M; p.N = N; p.ntaps = 1; p.kb_main = (K + 63) / 64; p.kb_aux = 0;
+    p.num_m_tiles = (M + TILE_M - 1) / TILE_M;
+    const int bn = pick_bn(N, {256, 128});
+    if (!bn) return set_error("linear: N=%d must be a multiple of 128", N);
+    p.num_n_tiles = N / bn;
+    p.out0 = out; p.bias = bias; p.vec1 = v1; p.ldo = ldo; p.T = T; p.W = gridw;
+    CUtensorMap ma, mb;
+    MG_TRY(make_map_2d(&ma, A, K, M, lda, TILE_M));
+    MG_TRY(make_map_2d(&mb, W, K, N, lda, bn));
+    const bool bf16 = e->bf16; const int sms = e->num_sms;
+    pl->ops.push_back([=](cudaStream_t st) { return launch_umma(bn, AMODE_ROWS, epi, bf16, ma, ma, mb, p, sms, st); });
+    return 0;
+}
+
+struct StackBufs {     // per-level scratch maps of one ConvStack
+    std::vector<void*> x_raw, x_relu, y_relu, t_up;
+};
+
+static int plan_stack(moge_engine* e, Plan* pl, const moge_stack_config_t& sc, const StackW& sw, bool is_neck, int B, int h,
+                      int w, float su, float sv, StackBufs& sb, const std::vector<void*>& neck_out, void* x0_raw, void* x0_relu,
+                      void* lowres_out) {
+    const int L = sc.num_levels;
+    const int* C = sc.dim_res_blocks;
+    void* x_raw = x0_raw;
+    void* x_relu = x0_relu;
+    for (int l = 0; l < L; ++l) {
+        const Level g = level_geom(h, w, l);
+        const int nres = sc.num_res_blocks[l];
+        for (int r = 0; r < nres; ++r) {
+            // y = conv3(relu(x)) -> only relu(y) is ever consumed
+            MG_TRY(add_conv(e, pl, sw.res[l][2 * r], x_relu, nullptr, g, B, EPI_DEC, nullptr, sb.y_relu[l], nullptr, g, C[l], false, false, 0, 0));
+            // x = x + conv3(relu(y))
+            void* nraw = (x_raw == sb.x_raw[l]) ? sb.t_up[l] : sb.x_raw[l];     // ping-pong between two raw maps
+            MG_TRY(add_conv(e, pl, sw.res[l][2 * r + 1], sb.y_relu[l], nullptr, g, B, EPI_DEC, nraw, (r + 1 < nres) ? x_relu : nullptr, x_raw, g, C[l], false, false, 0, 0));
+            x_raw = nraw;
+        }
+        if (is_neck) const_cast<std::vector<void*>&>(neck_out)[l] = x_raw;
+        if (l == L - 1) break;
+        const Level gn = level_geom(h, w, l + 1);
+        const bool tail = !is_neck && (l + 1 == L - 1);
+        const void* conv_src;
+        if (sc.resamplers[l] == MOGE_RESAMPLE_CONV_TRANSPOSE) {
+            MG_TRY(add_conv(e, pl, sw.convT[l], x_raw, nullptr, g, B, EPI_DEC, sb.t_up[l + 1], nullptr, nullptr, gn, C[l + 1], true, false, 0, 0));
+            conv_src = sb.t_up[l + 1];
+        } else {
+            void* up = sb.t_up[l + 1];
+            const bool bf16 = e->bf16;
+            const int Cl = C[l];
+            void* src = x_raw;
+            pl->ops.push_back([=](cudaStream_t st) { return launch_upsample2x(src, up, B, g.H, g.W, g.Hp, g.Wp, gn.Hp, gn.Wp, Cl, bf16, st); });
+            conv_src = up;
+        }
+        if (tail) {
+            MG_TRY(add_conv(e, pl, sw.headout, conv_src, nullptr, gn, B, EPI_HEADOUT, lowres_out, nullptr, neck_out[l + 1], gn, 0, false, false, 0, 0, sw.ncomp, sw.waux));
+            break;
+        }
+        const bool need_relu = sc.num_res_blocks[l + 1] > 0;
+        MG_TRY(add_conv(e, pl, sw.post[l], conv_src, is_neck ? nullptr : neck_out[l + 1], gn, B, EPI_DEC, sb.x_raw[l + 1],
+                        need_relu ? sb.x_relu[l + 1] : nullptr, nullptr, gn, C[l + 1], false, is_neck, su, sv));
+        x_raw = sb.x_raw[l + 1];
+        x_relu = sb.x_relu[l + 1];
+    }
+    return 0;
+}
+
+static int build_plan(moge_engine* e, Plan* pl, bool dry, size_t* bytes_out) {
+    const moge_config_t& c = e->cfg;
+    const int B = pl->B, h = pl->h, w = pl->w, H = pl->H, W = pl->W;
+    const int D = c.embed_dim, T = h * w, N = T + 1, M = B * N;
+    const bool bf16 = e->bf16;
+    WsAlloc ws(dry ? nullptr : pl->ws);
+    // ---- encoder buffers
+    void* patches = ws.take(static_cast<size_t>(B) * T * 592 * 2);
+    float* x = static_cast<float*>(ws.take(static_cast<size_t>(M) * D * 4));
+    void* ln = ws.take(static_cast<size_t>(M) * D * 2);
+    void* qkv = ws.take(static_cast<size_t>(M) * 3 * D * 2);
+    void* att = ws.take(static_cast<size_t>(M) * D * 2);
+    void* hid = ws.take(static_cast<size_t>(M) * 4 * D * 2);
+    void* taps = ws.take(static_cast<size_t>(B) * T * c.num_taps * D * 2);
+    float* cls = static_cast<float*>(ws.take(static_cast<size_t>(B) * D * 4));
+    float* mlp_scratch = static_cast<float*>(ws.take(static_cast<size_t>(2) * B * 4096 * 4));
+    // ---- decoder buffers
+    const int L = c.neck.num_levels;
+    std::vector<void*> neck_out(L, nullptr);
+    auto alloc_stack = [&](const moge_stack_config_t& sc, StackBufs& sb) {
+        sb.x_raw.assign(L, nullptr); sb.x_relu.assign(L, nullptr); sb.y_relu.assign(L, nullptr); sb.t_up.assign(L, nullptr);
+        for (int l = 0; l < L; ++l) {
+            const Level g = level_geom(h, w, l);
+            const int Cl = sc.dim_res_blocks[l];
+            sb.x_raw[l] = ws.take(map_bytes(g, B, Cl));
+            if (sc.num_res_blocks[l] > 0) {
+                sb.x_relu[l] = ws.take(map_bytes(g, B, Cl));
+                sb.y_relu[l] = ws.take(map_bytes(g, B, Cl));
+            }
+            // t_up[l]: resampler output feeding the 3x3 conv of level l (channels: convT -> C[l], bilinear -> C[l-1]);
+            // doubles as the second raw map of the residual ping-pong.
+            int ct = Cl;
+            if (l > 0 && sc.resamplers[l - 1] == MOGE_RESAMPLE_BILINEAR) ct = std::max(Cl, sc.dim_res_blocks[l - 1]);
+            sb.t_up[l] = ws.take(map_bytes(g, B, ct));
+        }
+    };
+    StackBufs nb, hb;
+    alloc_stack(c.neck, nb);
+    // neck outputs must survive all heads: the neck's final x per level is whichever ping-pong map holds it (kept).
+    bool any_head = false;
+    for (int i = 0; i < 3; ++i) any_head |= head_cfg(e, i)->present != 0;
+    if (any_head) alloc_stack(*head_cfg(e, c.points_head.present ? 0 : c.normal_head.present ? 1 : 2), hb);
+    const Level gl = level_geom(h, w, L - 1);
+    float4* pts_lr = c.points_head.present ? static_cast<float4*>(ws.take(static_cast<size_t>(B) * gl.H * gl.W * 16)) : nullptr;
+    float4* nrm_lr = c.normal_head.present ? static_cast<float4*>(ws.take(static_cast<size_t>(B) * gl.H * gl.W * 16)) : nullptr;
+    float* msk_lr = c.mask_head.present ? static_cast<float*>(ws.take(static_cast<size_t>(B) * gl.H * gl.W * 4)) : nullptr;
+    if (bytes_out) *bytes_out = ws.off + 1024;
+    if (dry) return 0;
+    if (ws.off > pl->ws_bytes) return set_error("workspace too small: need %zu bytes, got %zu", ws.off, pl->ws_bytes);
+
+    const float aspect = static_cast<float>(W) / H;
+    const float su = aspect / sqrtf(1.f + aspect * aspect), sv = 1.f / sqrtf(1.f + aspect * aspect);
+    Plan* P = pl;
+    // ---- K1: resize + normalise + patchify (reads the image pointer bound at forward time)
+    pl->ops.push_back([=](cudaStream_t st) { return launch_preprocess(P->image, P->image_dtype, B, H, W, h, w, patches, 592, bf16, st); });
+    // ---- K2/K3: patch embed + pos embed; cls rows
+    MG_TRY(add_linear(e, pl, patches, B * T, 592, 592, e->w_patch, D, EPI_PATCH, x, nullptr, pl->pos_table, D, T, w));
+    pl->ops.push_back([=](cudaStream_t st) { return launch_init_cls(x, P->cls_row, B, N, D, st); });
+    // ---- transformer blocks
+    int tap_idx = 0;
+    for (int i = 0; i < c.depth; ++i) {
+        const moge_engine::Blk& b = e->blk[i];
+        pl->ops.push_back([=](cudaStream_t st) { return launch_layernorm(x, b.ln1g, b.ln1b, ln, M, D, D, 0, 0, N, nullptr, bf16, st); });
+        MG_TRY(add_linear(e, pl, ln, M, D, D, b.wqkv, 3 * D, EPI_STORE16, qkv, b.bqkv, nullptr, 3 * D));
+        {
+            CUtensorMap mq;
+            MG_TRY(make_map_3d(&mq, qkv, 3 * D, N, B, 128));
+            const int heads = c.num_heads;
+            pl->ops.push_back([=](cudaStream_t st) { return launch_attention(mq, att, B, N, D, heads, bf16, st); });
+        }
+        MG_TRY(add_linear(e, pl, att, M, D, D, b.wproj, D, EPI_RESID, x, b.bproj, b.g1, D));
+        pl->ops.push_back([=](cudaStream_t st) { return launch_layernorm(x, b.ln2g, b.ln2b, ln, M, D, D, 0, 0, N, nullptr, bf16, st); });
+        MG_TRY(add_linear(e, pl, ln, M, D, D, b.wfc1, 4 * D, EPI_GELU16, hid, b.bfc1, nullptr, 4 * D));
+        MG_TRY(add_linear(e, pl, hid, M, 4 * D, 4 * D, b.wfc2, D, EPI_RESID, x, b.bfc2, b.g2, D));
+        if (tap_idx < c.num_taps && c.taps[tap_idx] == i) {
+            const int j = tap_idx++;
+            const bool lasttap = (j == c.num_taps - 1);
+            const int ld = c.num_taps * D;
+            const float* ng = e->norm_g; const float* nbv = e->norm_b;
+            pl->ops.push_back([=](cudaStream_t st) {
+                return launch_layernorm(x, ng, nbv, taps, M, D, ld, j * D, 1, N, lasttap ? cls : nullptr, bf16, st);
+            });
+        }
+    }
+    if (tap_idx != c.num_taps) return set_error("intermediate_layers must be increasing block indices < depth");
+    // ---- scale head
+    if (c.scale_head_layers > 0) {
+        std::vector<const float*> mw = e->mlp_w, mb = e->mlp_b;
+        std::vector<int> dims(c.scale_head_dims, c.scale_head_dims + c.scale_head_layers + 1);
+        const int nl = c.scale_head_layers;
+        for (int d : dims) if (d > 4096) return set_error("scale head width %d > 4096", d);
+        pl->ops.push_back([=](cudaStream_t st) {
+            if (!P->scale) return 0;
+            return launch_scale_head(cls, mw.data(), mb.data(), dims.data(), nl, B, P->scale, mlp_scratch, st);
+        });
+    }
+    // ---- neck level 0: folded projection GEMM over the concatenated taps (+UV rank-2 term) -> padded NHWC
+    {
+        const Level g0 = level_geom(h, w, 0);
+        const ConvW& f = e->fold0;
+        UmmaParams p{};
+        p.M = B * T; p.N = f.N; p.ntaps = 1; p.kb_main = f.Ktot / 64; p.kb_aux = 0;
+        if (f.Ktot % 64) return set_error("num_taps*embed_dim must be a multiple of 64");
+        p.num_m_tiles = (p.M + TILE_M - 1) / TILE_M;
+        const int bn = pick_bn(f.N, {256, 128});
+        if (!bn) return set_error("neck width %d must be a multiple of 128", f.N);
+        p.num_n_tiles = f.N / bn;
+        p.B = B; p.H = h; p.W = w; p.T = T;
+        p.out0 = nb.x_raw[0]; p.out1 = c.neck.num_res_blocks[0] > 0 ? nb.x_relu[0] : nullptr;
+        p.bias = f.bias; p.vec1 = f.wu; p.vec2 = f.wv; p.ldo = f.N;
+        p.Ho = g0.H; p.Wo = g0.W; p.Hop = g0.Hp; p.Wop = g0.Wp; p.su = su; p.sv = sv;
+        CUtensorMap ma, mb;
+        MG_TRY(make_map_2d(&ma, taps, f.Ktot, p.M, f.Ktot, TILE_M));
+        MG_TRY(make_map_2d(&mb, f.w, f.Ktot, f.N, f.Ktot, bn));
+        const int sms = e->num_sms;
+        pl->ops.push_back([=](cudaStream_t st) { return launch_umma(bn, AMODE_ROWS, EPI_DEC, bf16, ma, ma, mb, p, sms, st); });
+    }
+    MG_TRY(plan_stack(e, pl, c.neck, e->neck, true, B, h, w, su, sv, nb, neck_out, nb.x_raw[0], nb.x_relu[0], nullptr));
+    // ---- heads
+    for (int i = 0; i < 3; ++i) {
+        const moge_stack_config_t& sc = *head_cfg(e, i);
+        if (!sc.present) continue;
+        const Level g0 = level_geom(h, w, 0);
+        const StackW& sw = e->heads[i];
+        MG_TRY(add_conv(e, pl, sw.in0, neck_out[0], nullptr, g0, B, EPI_DEC, hb.x_raw[0], sc.num_res_blocks[0] > 0 ? hb.x_relu[0] : nullptr,
+                        nullptr, g0, sc.dim_res_blocks[0], false, false, 0, 0));
+        void* lowres = i == 0 ? static_cast<void*>(pts_lr) : i == 1 ? static_cast<void*>(nrm_lr) : static_cast<void*>(msk_lr);
+        MG_TRY(plan_stack(e, pl, sc, sw, false, B, h, w, su, sv, hb, neck_out, hb.x_raw[0], hb.x_relu[0], lowres));
+    }
+    // ---- K17 fused resize + remap
+    {
+        const int remap = c.remap_output;
+        pl->ops.push_back([=](cudaStream_t st) {
+            return launch_head_output(P->points ? pts_lr : nullptr, P->normal ? nrm_lr : nullptr, P->mask ? msk_lr : nullptr, B, gl.H, gl.W,
+                                      H, W, remap, P->points, P->normal, P->mask, st);
+        });
+    }
+    return 0;
+}
+
+static int get_plan(moge_engine* e, int B, int H, int W, int h, int w, void* ws, size_t ws_bytes, Plan** out, cudaStream_t st) {
+    for (auto& p : e->plans)
+        if (p->B == B && p->H == H && p->W == W && p->h == h && p->w == w && p->ws == ws) {
+            *out = p.get();
+            return 0;
+        }
+    if (e->plans.size() >= 16) e->plans.erase(e->plans.begin());
+    std::unique_ptr<Plan> pl(new Plan());
+    pl->B = B; pl->H = H; pl->W = W; pl->h = h; pl->w = w; pl->ws = ws; pl->ws_bytes = ws_bytes;
+    const int D = e->cfg.embed_dim;
+    MG_TRY(e->alloc(reinterpret_cast<void**>(&pl->pos_table), static_cast<size_t>(h) * w * D * 4));
+    MG_TRY(e->alloc(reinterpret_cast<void**>(&pl->cls_row), D * 4));
+    MG_TRY(launch_pos_table(e->pos_embed, e->cls_token, e->patch_bias, D, h, w, pl->pos_table, pl->cls_row, st));
+    MG_TRY(build_plan(e, pl.get(), false, nullptr));
+    *out = pl.get();
+    e->plans.push_back(std::move(pl));
+    return 0;
+}
+
+static int validate_cfg(const moge_config_t& c) {
+    if (c.embed_dim <= 0 || c.embed_dim % 128 || c.embed_dim > 1024) return set_error("embed_dim=%d unsupported (multiple of 128, <= 1024)", c.embed_dim);
+    if (c.num_heads * 64 != c.embed_dim) return set_error("head_dim must be 64 (embed_dim=%d, heads=%d)", c.embed_dim, c.num_heads);
+    if (c.num_taps <= 0 || c.num_taps > MOGE_MAX_TAPS) return set_error("num_taps=%d out of range", c.num_taps);
+    if (c.compute_dtype != MOGE_F16 && c.compute_dtype != MOGE_BF16) return set_error("compute_dtype must be MOGE_F16 or MOGE_BF16");
+    if (c.neck.num_levels < 2 || c.neck.num_levels > MOGE_MAX_LEVELS) return set_error("neck.num_levels=%d out of range", c.neck.num_levels);
+    const moge_stack_config_t* first = nullptr;
+    for (const moge_stack_config_t* s : {&c.points_head, &c.normal_head, &c.mask_head}) {
+        if (!s->present) continue;
+        if (s->num_levels != c.neck.num_levels) return set_error("head and neck level counts differ");
+        for (int l = 0; l < s->num_levels; ++l) {
+            if (s->dim_res_blocks[l] != c.neck.dim_res_blocks[l]) return set_error("head widths must equal neck widths");
+            if (first && (s->num_res_blocks[l] != first->num_res_blocks[l] || s->resamplers[l] != first->resamplers[l]))
+                return set_error("all heads must share one residual-block / resampler layout");
+        }
+        if (!first) first = s;
+    }
+    return 0;
+}
+
+}  // namespace mg
+
+// ================================================================================================ C ABI
+extern "C" {
+
+const char* moge_last_error(void) { return mg::last_error(); }
+const char* moge_version(void) { return "moge_b200 0.1.0 sm_100a"; }
+
+int moge_engine_create(const moge_config_t* cfg, int device, moge_engine_t** out) {
+    if (!cfg || !out) return set_error("null argument");
+    MG_TRY(validate_cfg(*cfg));
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return set_error("no CUDA device: moge_b200 has no CPU fallback");
+    CUDA_TRY(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) return set_error("device %d is sm_%d%d; libmoge_b200 contains sm_100a code only", device, prop.major, prop.minor);
+    moge_engine* e = new moge_engine();
+    e->cfg = *cfg; e->device = device; e->num_sms = prop.multiProcessorCount; e->bf16 = cfg->compute_dtype == MOGE_BF16;
+    *out = e;
+    return 0;
+}
+
+void moge_engine_destroy(moge_engine_t* e) {
+    if (!e) return;
+    cudaSetDevice(e->device);
+    cudaDeviceSynchronize();
+    for (void* p : e->owned) cudaFree(p);
+    for (auto& kv : e->raw) if (kv.second.p) cudaFree(kv.second.p);
+    delete e;
+}
+
+int moge_engine_set_weight(moge_engine_t* e, const char* key, const void* dev_ptr, const int64_t* shape, int ndim, int dtype, void* stream) {
+    if (!e || !key || !dev_ptr) return set_error("null argument");
+    if (e->finalized) return set_error("engine already finalized");
+    if (dtype != MOGE_F32 && dtype != MOGE_F16 && dtype != MOGE_BF16) return set_error("weight '%s': unsupported dtype %d", key, dtype);
+    CUDA_TRY(cudaSetDevice(e->device));
+    RawWeight rw;
+    rw.numel = 1;
+    for (int i = 0; i < ndim; ++i) { rw.shape.push_back(shape[i]); rw.numel *= static_cast<size_t>(shape[i]); }
+    // squeeze leading singleton dims of parameter-like tensors so shape checks see the logical shape
+    CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&rw.p), std::max<size_t>(rw.numel, 4) * 4));
+    const int blocks = static_cast<int>(std::min<size_t>((rw.numel + 255) / 256, 148 * 8));
+    to_f32_kernel<<<std::max(blocks, 1), 256, 0, static_cast<cudaStream_t>(stream)>>>(dev_ptr, dtype, rw.p, rw.numel);
+    CUDA_TRY(cudaGetLastError());
+    auto it = e->raw.find(key);
+    if (it != e->raw.end() && it->second.p) cudaFree(it->second.p);
+    e->raw[key] = rw;
+    return 0;
+}
+
+int moge_engine_finalize(moge_engine_t* e, void* stream) {
+    if (!e) return set_error("null engine");
+    if (e->finalized) return 0;
+    CUDA_TRY(cudaSetDevice(e->device));
+    return finalize(e, static_cast<cudaStream_t>(stream));
+}
+
+int moge_engine_workspace_bytes(moge_engine_t* e, int B, int H, int W, int h, int w, size_t* bytes) {
+    if (!e || !bytes) return set_error("null argument");
+    if (B <= 0 || h <= 0 || w <= 0 || H <= 0 || W <= 0) return set_error("bad shape B=%d H=%d W=%d h=%d w=%d", B, H, W, h, w);
+    Plan pl;
+    pl.B = B; pl.H = H; pl.W = W; pl.h = h; pl.w = w; pl.ws = nullptr; pl.ws_bytes = 0;
+    return build_plan(e, &pl, true, bytes);
+}
+
+int moge_engine_forward(moge_engine_t* e, const void* image, int image_dtype, int B, int H, int W, int h, int w, void* workspace,
+                        size_t workspace_bytes, float* points, float* normal, float* mask_prob, float* metric_scale, void* stream) {
+    if (!e || !image || !workspace) return set_error("null argument");
+    if (!e->finalized) return set_error("engine not finalized");
+    if (B <= 0 || h <= 0 || w <= 0 || H <= 0 || W <= 0) return set_error("bad shape B=%d H=%d W=%d h=%d w=%d", B, H, W, h, w);
+    if (reinterpret_cast<uintptr_t>(workspace) & 1023) return set_error("workspace must be 1024-byte aligned");
+    if (points && !e->cfg.points_head.present) return set_error("points requested but the model has no points head");
+    if (normal && !e->cfg.normal_head.present) return set_error("normal requested but the model has no normal head");
+    if (mask_prob && !e->cfg.mask_head.present) return set_error("mask requested but the model has no mask head");
+    if (metric_scale && e->cfg.scale_head_layers == 0) return set_error("metric_scale requested but the model has no scale head");
+    CUDA_TRY(cudaSetDevice(e->device));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    Plan* pl;
+    MG_TRY(get_plan(e, B, H, W, h, w, workspace, workspace_bytes, &pl, st));
+    pl->image = image; pl->image_dtype = image_dtype;
+    pl->points = points; pl->normal = normal; pl->mask = mask_prob; pl->scale = metric_scale;
+    for (auto& op : pl->ops) MG_TRY(op(st));
+    return 0;
+}
+
+int moge_recover_focal_shift(const float* points, const float* mask_prob, const uint8_t* mask_u8, int B, int H, int W,
+                             const float* focal_in, float* focal_out, float* shift_out, void* stream) {
+    if (!points || !focal_out || !shift_out) return set_error("null argument");
+    return launch_focal_shift(points, mask_prob, mask_u8, B, H, W, focal_in, focal_out, shift_out, static_cast<cudaStream_t>(stream));
+}
+
+int moge_postprocess(float* points, const float* normal_in, const float* mask_prob, const float* metric_scale, const float* focal,
+                     const float* shift, int B, int H, int W, int force_projection, int apply_mask, float* depth, float* normal_out,
+                     uint8_t* mask_out, float* intrinsics, void* stream) {
+    if (!points || !focal || !shift || !depth || !intrinsics) return set_error("null argument");
+    if (normal_in && !normal_out) return set_error("normal_out required when normal_in is given");
+    return launch_postprocess(points, normal_in, mask_prob, metric_scale, focal, shift, B, H, W, force_projection, apply_mask, depth,
+                              normal_out, mask_out, intrinsics, static_cast<cudaStream_t>(stream));
+}
+
+// ---------------------------------------------------------------------------------- operator-level entry points
+static int dev_sms() {
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    return sms;
+}
+
+int moge_op_linear(const void* x, const void* w, const float* bias, const float* gamma, void* out, int M, int N, int K, int epi,
+                   int dtype, void* stream) {
+    if (K % 8) return set_error("op_linear: K must be a multiple of 8");
+    const int bn = pick_bn(N, {256, 128});
+    if (!bn) return set_error("op_linear: N must be a multiple of 128");
+    if (epi < 0 || epi > 2) return set_error("op_linear: epi must be 0..2");
+    UmmaParams p{};
+    p.M = M; p.N = N; p.ntaps = 1; p.kb_main = (K + 63) / 64;
+    p.num_m_tiles = (M + TILE_M - 1) / TILE_M; p.num_n_tiles = N / bn;
+    p.out0 = out; p.bias = bias; p.vec1 = gamma; p.ldo = N;
+    CUtensorMap ma, mb;
+    MG_TRY(make_map_2d(&ma, x, K, M, K, TILE_M));
+    MG_TRY(make_map_2d(&mb, w, K, N, K, bn));
+    return launch_umma(bn, AMODE_ROWS, epi, dtype == MOGE_BF16, ma, ma, mb, p, dev_sms(), static_cast<cudaStream_t>(stream));
+}
+
+int moge_op_attention(const void* qkv, void* out, int B, int N, int D, int heads, int dtype, void* stream) {
+    CUtensorMap mq;
+    MG_TRY(make_map_3d(&mq, qkv, 3 * static_cast<uint64_t>(D), N, B, 128));
+    return launch_attention(mq, out, B, N, D, heads, dtype == MOGE_BF16, static_cast<cudaStream_t>(stream));
+}
+
+int moge_op_layernorm(const float* x, const float* gamma, const float* beta, void* out, int rows, int D, int dtype, void* stream) {
+    return launch_layernorm(x, gamma, beta, out, rows, D, D, 0, 0, 1, nullptr, dtype == MOGE_BF16, static_cast<cudaStream_t>(stream));
+}
+
+int moge_op_conv(const void* x, const float* w, const float* bias, const void* skip, void* out_raw, void* out_relu, int B, int H, int W,
+                 int Cin, int Cout, int taps, int shuffle, int dtype, void* stream) {
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const bool bf16 = dtype == MOGE_BF16;
+    if (Cin % 64) return set_error("op_conv: Cin must be a multiple of 64");
+    if (taps != 1 && taps != 9) return set_error("op_conv: taps must be 1 or 9");
+    if (shuffle && taps != 1) return set_error("op_conv: shuffle requires taps=1");
+    const int N = shuffle ? 4 * Cout : Cout;
+    const int bn = pick_bn(N, {256, 128, 64, 32});
+    if (!bn) return set_error("op_conv: Cout must be a multiple of 32");
+    const int Ktot = taps * Cin;
+    void* wp = nullptr;
+    CUDA_TRY(cudaMalloc(&wp, static_cast<size_t>(N) * Ktot * 2));
+    int rc = shuffle ? launch_pack_convT(w, wp, bf16, Cin, Cout, st) : launch_pack_conv(w, wp, bf16, Cout, Cin, taps, Ktot, 0, st);
+    if (rc == 0) {
+        Level gs{H, W, std::max(H + 2, TILE_PH), std::max(W + 2, TILE_PW)};
+        Level go = gs;
+        if (shuffle) go = Level{2 * H, 2 * W, std::max(2 * H + 2, TILE_PH), std::max(2 * W + 2, TILE_PW)};
+        UmmaParams p{};
+        p.N = N; p.ntaps = taps; p.kb_main = Cin / 64; p.kb_aux = 0;
+        p.B = B; p.H = H; p.W = W;
+        p.tiles_x = (W + TILE_PW - 1) / TILE_PW; p.tiles_y = (H + TILE_PH - 1) / TILE_PH;
+        p.num_m_tiles = B * p.tiles_x * p.tiles_y; p.num_n_tiles = N / bn;
+        p.out0 = out_raw; p.out1 = out_relu; p.bias = bias; p.skip = skip; p.ldo = Cout;
+        p.Ho = go.H; p.Wo = go.W; p.Hop = go.Hp; p.Wop = go.Wp; p.shuffle = shuffle;
+        CUtensorMap ma, mb;
+        rc = make_map_nhwc(&ma, x, Cin, gs.Wp, gs.Hp, B);
+        if (rc == 0) rc = make_map_2d(&mb, wp, Ktot, N, Ktot, bn);
+        if (rc == 0) rc = launch_umma(bn, AMODE_TILES, EPI_DEC, bf16, ma, ma, mb, p, dev_sms(), st);
+    }
+    cudaStreamSynchronize(st);
+    cudaFree(wp);
+    return rc;
+}
+
+}  // extern "C"

@@ -1,0 +1,82 @@
+// Internal host-side declarations shared by the .cu translation units of libmoge_b200.so.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stddef.h>
+
+namespace mg {
+
+// Thread-local error message behind moge_last_error(); returns -1 so callers can `return set_error(...)`.
+int set_error(const char* fmt, ...);
+
+#define CUDA_TRY(expr)                                                                                   \
+    do {                                                                                                 \
+        cudaError_t _e = (expr);                                                                         \
+        if (_e != cudaSuccess)                                                                           \
+            return ::mg::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+    } while (0)
+#define MG_TRY(expr)                \
+    do {                            \
+        int _r = (expr);            \
+        if (_r != 0) return _r;     \
+    } while (0)
+
+// ---- TMA descriptors (driver entry point resolved at run time; no link-time libcuda dependency)
+// 16-bit element maps with a 64-element (128-byte) inner box and SWIZZLE_128B.
+int make_map_2d(CUtensorMap* m, const void* base, uint64_t cols, uint64_t rows, uint64_t row_pitch_elems, uint32_t box_rows);
+int make_map_3d(CUtensorMap* m, const void* base, uint64_t cols, uint64_t rows, uint64_t batch, uint32_t box_rows);
+// padded NHWC image [B, Hp, Wp, C]: box {64 ch, 16 px, 8 rows, 1}
+int make_map_nhwc(CUtensorMap* m, const void* base, uint64_t C, uint64_t Wp, uint64_t Hp, uint64_t B);
+
+struct UmmaParams;
+// bn in {16,32,64,128,256}; amode/epi as in umma_kernel.cuh
+int launch_umma(int bn, int amode, int epi, bool bf16, const CUtensorMap& a, const CUtensorMap& aux, const CUtensorMap& b,
+                const UmmaParams& p, int num_sms, cudaStream_t st);
+
+int launch_attention(const CUtensorMap& mapQKV, void* out, int B, int N, int D, int heads, bool bf16, cudaStream_t st);
+
+// ---- small kernels (elementwise.cu)
+// K1: antialiased bilinear resize to (14h,14w) + ImageNet normalise + patchify -> A[B*T, Kp] (16-bit, Kp = 592)
+int launch_preprocess(const void* image, int image_dtype, int B, int H, int W, int h, int w, void* patches, int Kp,
+                      bool bf16, cudaStream_t st);
+// K3: table[t, d] = bicubic(pos_embed grid)[t, d] + patch bias[d]  (fp32), cls_row[d] = cls_token[d] + pos_embed[0, d]
+int launch_pos_table(const float* pos_embed, const float* cls_token, const float* patch_bias, int D, int h, int w,
+                     float* table, float* cls_row, cudaStream_t st);
+int launch_init_cls(float* x, const float* cls_row, int B, int N, int D, cudaStream_t st);
+// LayerNorm eps=1e-6 over D: fp32 in -> 16-bit out.  Row r of the input maps to out row r (ld_out elements per row).
+// mode 0: plain (all rows).  mode 1 (taps): skip cls rows; patch token (b,t) -> out[(b*T+t)*ld_out + col_off + d];
+// the cls row of each image is written (fp32) to cls_out[b, D] when cls_out != null.
+int launch_layernorm(const float* x, const float* gamma, const float* beta, void* out, int rows, int D, int ld_out,
+                     int col_off, int mode, int tokens_per_image, float* cls_out, bool bf16, cudaStream_t st);
+// scale head: metric_scale[b] = exp(MLP(cls[b]))
+int launch_scale_head(const float* cls, const float* const* w, const float* const* bias, const int* dims, int nlayers,
+                      int B, float* out, float* scratch, cudaStream_t st);
+// bilinear x2 (align_corners=False) NHWC padded -> NHWC padded (+ replicated border)
+int launch_upsample2x(const void* src, void* dst, int B, int H, int W, int Hp, int Wp, int Hop, int Wop, int C, bool bf16,
+                      cudaStream_t st);
+// zero / replicate helpers
+int launch_fill_border(void* buf, int B, int H, int W, int Hp, int Wp, int C, cudaStream_t st);
+// K17: bilinear resize of the low-res head maps to (H,W) + remap -> points (B,H,W,3), normal (B,H,W,3), mask prob (B,H,W)
+int launch_head_output(const float4* pts_lr, const float4* nrm_lr, const float* msk_lr, int B, int Hl, int Wl, int H, int W,
+                       int remap_mode, float* points, float* normal, float* mask, cudaStream_t st);
+// K18
+int launch_focal_shift(const float* points, const float* mask_prob, const uint8_t* mask_u8, int B, int H, int W,
+                       const float* focal_in, float* focal_out, float* shift_out, cudaStream_t st);
+// K19
+int launch_postprocess(float* points, const float* normal_in, const float* mask_prob, const float* metric_scale,
+                       const float* focal, const float* shift, int B, int H, int W, int force_projection, int apply_mask,
+                       float* depth, float* normal_out, uint8_t* mask_out, float* intrinsics, cudaStream_t st);
+
+// ---- weight packing (pack.cu): generic strided gather/cast and a small fp32 GEMM for load-time folds
+int launch_cast_2d(const void* src, int src_dtype, void* dst, bool bf16, int rows, int cols, int src_ld, int dst_ld,
+                   cudaStream_t st);
+// dst16[n, k_off + tap*Cin + ci] = W[n, ci, tap]  for conv weight (Cout, Cin, kh, kw) fp32
+int launch_pack_conv(const float* w, void* dst, bool bf16, int Cout, int Cin, int taps, int dst_ld, int k_off, cudaStream_t st);
+// dst16[(q*Cout + co), ci] = W[ci, co, q]  for ConvTranspose2d weight (Cin, Cout, 2, 2)
+int launch_pack_convT(const float* w, void* dst, bool bf16, int Cin, int Cout, cudaStream_t st);
+// C[M,N] (fp32, ldc) = A[M,K] (lda) * B[K,N] (ldb)  (+ C if accumulate)   -- load-time only, SIMT
+int launch_sgemm(const float* A, int lda, const float* B, int ldb, float* C, int ldc, int M, int N, int K, int accumulate,
+                 cudaStream_t st);
+
+}  // namespace mg

@@ -1,0 +1,358 @@
+// The one tensor-core kernel of the engine: a persistent, warp-specialised tcgen05 GEMM whose A operand is either
+// a row-major matrix (encoder linears) or an 8x16-pixel window of a padded NHWC image shifted by a filter tap
+// (decoder implicit-GEMM convolutions).  TMA -> 128B-swizzled smem ring -> tcgen05.mma (fp32 accumulators in
+// TMEM, double-buffered) -> fused epilogue straight from TMEM.
+//
+// Roles (warp-uniform): warp 0 = TMA producer (1 lane), warp 1 = MMA issuer (1 lane) + TMEM owner,
+// warps 2.. = epilogue (each warp owns the TMEM lane quarter (warp & 3); with 8 epilogue warps the two warps of a
+// quarter split the accumulator columns).
+//
+// Reference ops covered: K2 patch-embed, K4 qkv, K6 proj+LayerScale+residual, K7 fc1+GELU,
+// K8 fc2+LayerScale+residual, K9 tap projection sum, K10/K11 1x1 + UV, K12 ConvTranspose2d k2s2, K13/K14 3x3
+// replicate-padded conv with ReLU/residual, K17 head output projection.
+#pragma once
+#include "common.cuh"
+
+namespace mg {
+
+enum : int { AMODE_ROWS = 0, AMODE_TILES = 1 };
+enum : int {
+    EPI_STORE16 = 0,   // out16[row, col] = T(acc + bias[col])
+    EPI_GELU16 = 1,    // out16[row, col] = T(gelu_erf(acc + bias[col]))
+    EPI_RESID = 2,     // x32[row, col] += gamma[col] * (acc + bias[col])            (fp32 residual stream, in place)
+    EPI_PATCH = 3,     // x32[b*(T+1)+1+t, col] = acc + table[t, col]                (patch embed + pos embed)
+    EPI_DEC = 4,       // padded-NHWC decoder store: acc + bias (+ UV rank-2) (+ skip) -> raw and/or ReLU copies
+    EPI_HEADOUT = 5,   // BN=16: folded head output projection + folded 1x1 of the neck level-4 map -> fp32 maps
+};
+
+constexpr int TILE_M = 128;
+constexpr int TILE_K = 64;     // 64 x 16-bit = one 128-byte swizzle row
+constexpr int TILE_PW = 16;    // pixel tile = 8 rows x 16 columns
+constexpr int TILE_PH = 8;
+
+struct UmmaParams {
+    // GEMM shape
+    int M;                 // AMODE_ROWS: number of valid rows
+    int N;                 // total output columns (multiple of BN)
+    int ntaps;             // 1 (centre) or 9 (3x3)
+    int kb_main;           // 64-wide K blocks per tap from the main source
+    int kb_aux;            // 64-wide K blocks from the aux source (centre tap), appended after the taps
+    int num_m_tiles, num_n_tiles;
+    // pixel geometry (AMODE_TILES: of the A source; EPI_DEC/HEADOUT: output pixel grid derives from it)
+    int B, H, W;           // A-source unpadded size (AMODE_ROWS + EPI_DEC: the h x w token grid)
+    int tiles_x, tiles_y;
+    // epilogue operands
+    void* out0;            // EPI_STORE16/GELU16: T* ; EPI_RESID/PATCH: float* ; EPI_DEC: raw T* (or null) ; HEADOUT: float*
+    void* out1;            // EPI_DEC: ReLU copy T* (or null)
+    const float* bias;     // [N] (EPI_DEC shuffle: [C_out]); HEADOUT: [16]
+    const float* vec1;     // EPI_RESID: gamma[N]; EPI_PATCH: table[T, N]; EPI_DEC: wu[C] (or null); HEADOUT: waux[ncomp,32] (or null)
+    const float* vec2;     // EPI_DEC: wv[C]
+    const void* skip;      // EPI_DEC: residual input, same geometry as out ; HEADOUT: neck level-4 map (T*, 32 ch, padded)
+    int ldo;               // row pitch of out (elements): ROWS epilogues: N total; DEC: channels of the out buffer
+    int T;                 // EPI_PATCH / ROWS+EPI_DEC: tokens per image
+    int Ho, Wo, Hop, Wop;  // EPI_DEC/HEADOUT: output pixel grid and its padded allocation
+    int shuffle;           // EPI_DEC: 1 = ConvTranspose2d k2s2 pixel shuffle (Ho = 2H, Wo = 2W), N = 4*C_out
+    int ncomp;             // HEADOUT: 3 (float4 per pixel) or 1 (float per pixel)
+    float su, sv;          // UV half extents
+};
+
+template <int BN> struct UmmaCfg {
+    static constexpr int kStageBytes = TILE_M * 128 + BN * 128;
+    static constexpr int kStages = (BN >= 256) ? 4 : (BN >= 128) ? 6 : 8;
+    static constexpr int kEpiWarps = (BN >= 64) ? 8 : 4;
+    static constexpr int kThreads = 64 + 32 * kEpiWarps;
+    static constexpr int kTmemCols = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
+    static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+    static constexpr int kColsPerWarp = (kEpiWarps == 8) ? BN / 2 : BN;
+};
+
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+
+// 64-byte (32 x 16-bit) store of one pixel's channel chunk into a padded NHWC buffer, replicating into the 1-pixel
+// border when the pixel lies on the image edge (so that 3x3 taps of the consumer never need clamping).
+__device__ __forceinline__ void store_px_border(uint8_t* base, int b, int Y, int X, int Ho, int Wo, int Hop, int Wop,
+                                                int ld, int c0, const uint4* q) {
+    const int y0 = (Y == 0) ? 0 : Y + 1, y1 = (Y == Ho - 1) ? Y + 2 : Y + 1;
+    const int x0 = (X == 0) ? 0 : X + 1, x1 = (X == Wo - 1) ? X + 2 : X + 1;
+    for (int yy = y0; yy <= y1; ++yy)
+        for (int xx = x0; xx <= x1; ++xx) {
+            uint4* dst = reinterpret_cast<uint4*>(base + ((static_cast<size_t>(b) * Hop + yy) * Wop + xx) * ld * 2 + c0 * 2);
+            dst[0] = q[0]; dst[1] = q[1]; dst[2] = q[2]; dst[3] = q[3];
+        }
+}
+
+template <int BN, int AMODE, int EPI, bool BF16>
+__global__ void __launch_bounds__(UmmaCfg<BN>::kThreads, 1)
+umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapAux,
+            const __grid_constant__ CUtensorMap mapB, const UmmaParams p) {
+    using Cfg = UmmaCfg<BN>;
+    using H = H16<BF16>;
+    constexpr int S = Cfg::kStages;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + S * Cfg::kStageBytes);
+    uint64_t* empty = full + S;
+    uint64_t* tfull = empty + S;
+    uint64_t* tempty = tfull + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int total_tiles = p.num_m_tiles * p.num_n_tiles;
+    const int kb_taps = p.ntaps * p.kb_main;
+    const int kb_total = kb_taps + p.kb_aux;
+
+    if (threadIdx.x == 0) {
+        tma_prefetch_desc(&mapA);
+        tma_prefetch_desc(&mapB);
+        if (p.kb_aux) tma_prefetch_desc(&mapAux);
+        for (int s = 0; s < S; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], Cfg::kEpiWarps); }
+        fence_mbar_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, Cfg::kTmemCols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ================================================================== TMA producer
+        if (lane == 0) {
+            int s = 0; uint32_t ph = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                const int mt = tile / p.num_n_tiles, nt = tile % p.num_n_tiles;
+                int b = 0, x0 = 0, y0 = 0;
+                if (AMODE == AMODE_TILES) {
+                    const int per_img = p.tiles_x * p.tiles_y;
+                    b = mt / per_img;
+                    const int r = mt % per_img;
+                    y0 = (r / p.tiles_x) * TILE_PH;
+                    x0 = (r % p.tiles_x) * TILE_PW;
+                }
+                for (int i = 0; i < kb_total; ++i) {
+                    mbar_wait(&empty[s], ph ^ 1);
+                    uint8_t* sa = smem + s * Cfg::kStageBytes;
+                    uint8_t* sb = sa + TILE_M * 128;
+                    mbar_arrive_expect_tx(&full[s], Cfg::kStageBytes);
+                    if (AMODE == AMODE_ROWS) {
+                        tma_load_2d(sa, &mapA, &full[s], i * TILE_K, mt * TILE_M);
+                    } else if (i < kb_taps) {
+                        const int tap = i / p.kb_main, c = i % p.kb_main;
+                        const int tx = (p.ntaps == 9) ? tap % 3 : 1, ty = (p.ntaps == 9) ? tap / 3 : 1;
+                        tma_load_4d(sa, &mapA, &full[s], c * TILE_K, x0 + tx, y0 + ty, b);
+                    } else {
+                        tma_load_4d(sa, &mapAux, &full[s], (i - kb_taps) * TILE_K, x0 + 1, y0 + 1, b);
+                    }
+                    tma_load_2d(sb, &mapB, &full[s], i * TILE_K, nt * BN);
+                    if (++s == S) { s = 0; ph ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ================================================================== MMA issuer
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc(TILE_M, BN, BF16 ? 1u : 0u);
+            int s = 0; uint32_t ph = 0;
+            int it = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+                const int acc = it & 1;
+                const uint32_t aph = (it >> 1) & 1;
+                mbar_wait(&tempty[acc], aph ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * BN;
+                for (int i = 0; i < kb_total; ++i) {
+                    mbar_wait(&full[s], ph);
+                    tc_fence_after();
+                    const uint32_t sa = smem_u32(smem + s * Cfg::kStageBytes);
+                    const uint64_t adesc = make_sdesc_sw128(sa);
+                    const uint64_t bdesc = make_sdesc_sw128(sa + TILE_M * 128);
+#pragma unroll
+                    for (int k = 0; k < TILE_K / 16; ++k)
+                        umma_f16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (i | k) != 0);
+                    umma_commit(&empty[s]);
+                    if (++s == S) { s = 0; ph ^= 1; }
+                }
+                umma_commit(&tfull[acc]);
+            }
+        }
+    } else {
+        // ================================================================== epilogue
+        const int ew = warp - 2;
+        const int quarter = warp & 3;
+        const int col_begin = (Cfg::kEpiWarps == 8) ? (ew >> 2) * (BN / 2) : 0;
+        const int row = quarter * 32 + lane;
+        int it = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+            const int mt = tile / p.num_n_tiles, nt = tile % p.num_n_tiles;
+            const int acc = it & 1;
+            const uint32_t aph = (it >> 1) & 1;
+            // ---- row -> output coordinates
+            bool valid;
+            long grow = 0;
+            int b = 0, py = 0, px = 0;
+            if (AMODE == AMODE_ROWS) {
+                grow = static_cast<long>(mt) * TILE_M + row;
+                valid = grow < p.M;
+                if (EPI == EPI_DEC || EPI == EPI_PATCH) {
+                    b = static_cast<int>(grow / p.T);
+                    const int t = static_cast<int>(grow % p.T);
+                    py = t / p.W; px = t % p.W;
+                }
+            } else {
+                const int per_img = p.tiles_x * p.tiles_y;
+                b = mt / per_img;
+                const int r = mt % per_img;
+                py = (r / p.tiles_x) * TILE_PH + row / TILE_PW;
+                px = (r % p.tiles_x) * TILE_PW + row % TILE_PW;
+                valid = (py < p.H) && (px < p.W);
+            }
+            mbar_wait(&tfull[acc], aph);
+            tc_fence_after();
+            const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN + col_begin;
+
+            if (EPI == EPI_HEADOUT) {
+                float v[16];
+                tmem_ld16(t_addr, v);
+                tc_wait_ld();
+                if (valid) {
+                    float o[3] = {v[0] + p.bias[0], v[1] + p.bias[1], v[2] + p.bias[2]};
+                    if (p.vec1 != nullptr) {
+                        const uint4* src = reinterpret_cast<const uint4*>(
+                            static_cast<const uint8_t*>(p.skip) + ((static_cast<size_t>(b) * p.Hop + py + 1) * p.Wop + px + 1) * 64);
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            const uint4 u = src[q];
+                            const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                const float2 f = H::unpack(w[e]);
+                                const int c = q * 8 + e * 2;
+                                for (int k = 0; k < 3; ++k)
+                                    if (k < p.ncomp) o[k] += p.vec1[k * 32 + c] * f.x + p.vec1[k * 32 + c + 1] * f.y;
+                            }
+                        }
+                    }
+                    const size_t pix = (static_cast<size_t>(b) * p.Ho + py) * p.Wo + px;
+                    if (p.ncomp == 1) static_cast<float*>(p.out0)[pix] = o[0];
+                    else static_cast<float4*>(p.out0)[pix] = make_float4(o[0], o[1], o[2], 0.f);
+                }
+            } else {
+#pragma unroll 1
+                for (int c = 0; c < Cfg::kColsPerWarp; c += 32) {
+                    float v[32];
+                    tmem_ld32(t_addr + c, v);
+                    tc_wait_ld();
+                    const int col = nt * BN + col_begin + c;       // first global output column of this chunk
+                    if (!valid) {
+                        // nothing to store for padding rows (tcgen05.ld above stays warp-convergent)
+                    } else if (EPI == EPI_STORE16 || EPI == EPI_GELU16) {
+                        const float4* bp = reinterpret_cast<const float4*>(p.bias + col);
+                        uint4 q[4];
+                        uint32_t* qw = reinterpret_cast<uint32_t*>(q);
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const float4 bb = bp[j];
+                            float a0 = v[4 * j] + bb.x, a1 = v[4 * j + 1] + bb.y, a2 = v[4 * j + 2] + bb.z, a3 = v[4 * j + 3] + bb.w;
+                            if (EPI == EPI_GELU16) { a0 = gelu_erf(a0); a1 = gelu_erf(a1); a2 = gelu_erf(a2); a3 = gelu_erf(a3); }
+                            qw[2 * j] = H::pack(a0, a1);
+                            qw[2 * j + 1] = H::pack(a2, a3);
+                        }
+                        uint4* dst = reinterpret_cast<uint4*>(static_cast<typename H::T*>(p.out0) + grow * p.ldo + col);
+                        dst[0] = q[0]; dst[1] = q[1]; dst[2] = q[2]; dst[3] = q[3];
+                    } else if (EPI == EPI_RESID) {
+                        const float4* bp = reinterpret_cast<const float4*>(p.bias + col);
+                        const float4* gp = reinterpret_cast<const float4*>(p.vec1 + col);
+                        float4* xp = reinterpret_cast<float4*>(static_cast<float*>(p.out0) + grow * p.ldo + col);
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const float4 bb = bp[j], gg = gp[j];
+                            float4 x = xp[j];
+                            x.x += gg.x * (v[4 * j] + bb.x);
+                            x.y += gg.y * (v[4 * j + 1] + bb.y);
+                            x.z += gg.z * (v[4 * j + 2] + bb.z);
+                            x.w += gg.w * (v[4 * j + 3] + bb.w);
+                            xp[j] = x;
+                        }
+                    } else if (EPI == EPI_PATCH) {
+                        const int t = py * p.W + px;
+                        const float4* tp = reinterpret_cast<const float4*>(p.vec1 + static_cast<size_t>(t) * p.ldo + col);
+                        float4* xp = reinterpret_cast<float4*>(static_cast<float*>(p.out0) +
+                                                               (static_cast<size_t>(b) * (p.T + 1) + 1 + t) * p.ldo + col);
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const float4 tt = tp[j];
+                            xp[j] = make_float4(v[4 * j] + tt.x, v[4 * j + 1] + tt.y, v[4 * j + 2] + tt.z, v[4 * j + 3] + tt.w);
+                        }
+                    } else if (EPI == EPI_DEC) {
+                        int Y = py, X = px, co = col;
+                        if (p.shuffle) {
+                            const int q = col / p.ldo;            // ldo == C_out; a 32-column chunk never straddles q
+                            co = col - q * p.ldo;
+                            Y = 2 * py + (q >> 1);
+                            X = 2 * px + (q & 1);
+                        }
+                        const float4* bp = reinterpret_cast<const float4*>(p.bias + co);
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const float4 bb = bp[j];
+                            v[4 * j] += bb.x; v[4 * j + 1] += bb.y; v[4 * j + 2] += bb.z; v[4 * j + 3] += bb.w;
+                        }
+                        if (p.vec1 != nullptr) {
+                            const float uu = p.su * ((2 * X + 1) / static_cast<float>(p.Wo) - 1.0f);
+                            const float vv = p.sv * ((2 * Y + 1) / static_cast<float>(p.Ho) - 1.0f);
+                            const float4* up = reinterpret_cast<const float4*>(p.vec1 + co);
+                            const float4* vp = reinterpret_cast<const float4*>(p.vec2 + co);
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) {
+                                const float4 a = up[j], d = vp[j];
+                                v[4 * j] += a.x * uu + d.x * vv; v[4 * j + 1] += a.y * uu + d.y * vv;
+                                v[4 * j + 2] += a.z * uu + d.z * vv; v[4 * j + 3] += a.w * uu + d.w * vv;
+                            }
+                        }
+                        if (p.skip != nullptr) {
+                            const uint4* sp = reinterpret_cast<const uint4*>(
+                                static_cast<const uint8_t*>(p.skip) +
+                                (((static_cast<size_t>(b) * p.Hop + Y + 1) * p.Wop + X + 1) * p.ldo + co) * 2);
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                const uint4 u = sp[j];
+                                const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+                                for (int e = 0; e < 4; ++e) {
+                                    const float2 f = H::unpack(w[e]);
+                                    v[8 * j + 2 * e] += f.x; v[8 * j + 2 * e + 1] += f.y;
+                                }
+                            }
+                        }
+                        uint4 q[4];
+                        uint32_t* qw = reinterpret_cast<uint32_t*>(q);
+                        if (p.out0 != nullptr) {
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) qw[j] = H::pack(v[2 * j], v[2 * j + 1]);
+                            store_px_border(static_cast<uint8_t*>(p.out0), b, Y, X, p.Ho, p.Wo, p.Hop, p.Wop, p.ldo, co, q);
+                        }
+                        if (p.out1 != nullptr) {
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) qw[j] = H::pack(fmaxf(v[2 * j], 0.f), fmaxf(v[2 * j + 1], 0.f));
+                            store_px_border(static_cast<uint8_t*>(p.out1), b, Y, X, p.Ho, p.Wo, p.Hop, p.Wop, p.ldo, co, q);
+                        }
+                    }
+                    __syncwarp();
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty[acc]);
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, Cfg::kTmemCols);
+    }
+}
+
+}  // namespace mg

@@ -1,0 +1,31 @@
+// Host-side launch helper shared by the two instantiation units of umma_kernel.
+#pragma once
+#include "umma_kernel.cuh"
+#include "host_api.h"
+
+namespace mg {
+
+template <int BN, int AMODE, int EPI, bool BF16>
+int launch_umma_inst(const CUtensorMap& a, const CUtensorMap& aux, const CUtensorMap& b, const UmmaParams& p, int num_sms,
+                     cudaStream_t st) {
+    using Cfg = UmmaCfg<BN>;
+    auto kern = umma_kernel<BN, AMODE, EPI, BF16>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+        attr_set = true;
+    }
+    const int tiles = p.num_m_tiles * p.num_n_tiles;
+    if (tiles <= 0) return 0;
+    const int grid = tiles < num_sms ? tiles : num_sms;
+    kern<<<grid, Cfg::kThreads, Cfg::kSmemBytes, st>>>(a, aux, b, p);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+int launch_umma_rows(int bn, int epi, bool bf16, const CUtensorMap& a, const CUtensorMap& aux, const CUtensorMap& b,
+                     const UmmaParams& p, int num_sms, cudaStream_t st);
+int launch_umma_tiles(int bn, int epi, bool bf16, const CUtensorMap& a, const CUtensorMap& aux, const CUtensorMap& b,
+                      const UmmaParams& p, int num_sms, cudaStream_t st);
+
+}  // namespace mg

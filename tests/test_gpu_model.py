@@ -1,0 +1,123 @@
+"""-m gpu: end-to-end parity of the drop-in MoGeModel (engine) against the oracle port and the reference goldens.
+
+Tolerances: fp16 engine vs fp32 oracle rel-L2 <= 1e-3 per output of forward(); bf16 <= 1e-2."""
+import os
+
+import pytest
+import torch
+
+from moge.model.v2 import MoGeModel
+from moge_b200.configs import model_config, default_num_tokens
+from moge_b200.synthetic import make_state_dict, synthetic_images
+from oracle import moge_port
+from gpu_util import rel_l2
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+_models = {}
+
+
+def get_model(size, with_normal, seed, dtype=torch.float16):
+    key = (size, with_normal, seed, dtype)
+    if key not in _models:
+        cfg = model_config(size, with_normal)
+        sd = make_state_dict(cfg, seed)
+        m = MoGeModel(**cfg)
+        m.load_state_dict(sd)
+        m = m.to(DEV).eval()
+        if dtype == torch.bfloat16:
+            m = m.bfloat16()
+        _models.clear()
+        _models[key] = (m, cfg, sd)
+    return _models[key]
+
+
+def check_forward(out, ref, tol, s=1):
+    rep = {}
+    for k, r in ref.items():
+        got = out[k].cpu()
+        got = got[:, ::s, ::s] if got.dim() >= 3 else got
+        assert torch.isfinite(got).all(), k
+        rep[k] = rel_l2(got, r)
+    print("forward rel-L2:", {k: f"{v:.2e}" for k, v in rep.items()})
+    for k, v in rep.items():
+        assert v < tol, (k, rep)
+
+
+@pytest.mark.parametrize("name", ["vits_b1_126x168_t192", "vits_b2_140x98_t117", "vits_b1_70x70_t1369_native",
+                                  "vitb_b1_98x154_t150_nonormal", "vits_b1_224x224_default", "vitl_b1_112x140_t120"])
+def test_forward_and_infer_match_reference_golden(name, golden_dir):
+    gold = torch.load(os.path.join(golden_dir, name + ".pt"), weights_only=False)
+    meta = gold["meta"]
+    model, cfg, sd = get_model(meta["size"], meta["with_normal"], meta["seed"])
+    B, H, W = meta["shape"]
+    img = synthetic_images(B, H, W, meta["seed"]).to(DEV)
+    nt = meta["num_tokens"] or default_num_tokens(cfg["num_tokens_range"])
+    s = meta["stride"]
+    out = model.forward(img, nt)
+    torch.cuda.synchronize()
+    assert set(out.keys()) == set(gold["forward"].keys())
+    check_forward(out, gold["forward"], 1e-3, s)
+    inf = model.infer(img, num_tokens=meta["num_tokens"])
+    torch.cuda.synchronize()
+    ginf = gold["infer"]
+    assert set(inf.keys()) == set(ginf.keys())
+    m_ref = ginf["mask"]
+    m_got = inf["mask"].cpu()[:, ::s, ::s]
+    assert inf["mask"].dtype == torch.bool
+    agree = (m_got == m_ref).float().mean()
+    assert agree > 0.995, agree            # mask logits near 0 may flip under fp16
+    both = m_got & m_ref
+    rep = {"intrinsics": rel_l2(inf["intrinsics"], ginf["intrinsics"])}
+    for k in ("points", "depth", "normal"):
+        if k in ginf:
+            rep[k] = rel_l2(inf[k].cpu()[:, ::s, ::s][both], ginf[k][both])
+    print("infer rel-L2:", {k: f"{v:.2e}" for k, v in rep.items()}, "mask agreement", float(agree))
+    for k, v in rep.items():
+        assert v < 3e-3, (k, rep)         # infer() adds the focal/shift solve on top of the 1e-3 forward budget
+    assert torch.isinf(inf["points"].cpu()[~inf["mask"].cpu()]).all()
+
+
+def test_forward_matches_oracle_port_bf16():
+    model, cfg, sd = get_model("vits", True, 0, torch.bfloat16)
+    img = synthetic_images(1, 126, 168, 0)
+    ref = moge_port.forward(cfg, sd, img, 192)
+    out = model.forward(img.to(DEV), 192)
+    torch.cuda.synchronize()
+    check_forward(out, ref, 1e-2)
+
+
+def test_batch_invariance_and_squeeze():
+    model, cfg, sd = get_model("vits", True, 1)
+    img = synthetic_images(3, 84, 112, 21).to(DEV)
+    full = model.infer(img, num_tokens=150)
+    one = model.infer(img[1], num_tokens=150)
+    torch.cuda.synchronize()
+    assert one["points"].shape == (84, 112, 3) and one["intrinsics"].shape == (3, 3) and one["mask"].shape == (84, 112)
+    m = full["mask"][1] & one["mask"]
+    assert rel_l2(one["depth"][m], full["depth"][1][m]) < 1e-5
+    assert rel_l2(one["intrinsics"], full["intrinsics"][1]) < 1e-5
+
+
+def test_known_fov_branch_matches_port():
+    model, cfg, sd = get_model("vits", True, 1)
+    img = synthetic_images(2, 84, 112, 22)
+    ref = moge_port.infer(cfg, sd, img, num_tokens=150, fov_x=60.0)
+    out = model.infer(img.to(DEV), num_tokens=150, fov_x=60.0)
+    torch.cuda.synchronize()
+    assert rel_l2(out["intrinsics"], ref["intrinsics"]) < 1e-5
+    m = out["mask"].cpu() & ref["mask"]
+    assert rel_l2(out["depth"].cpu()[m], ref["depth"][m]) < 3e-3
+
+
+def test_from_pretrained_roundtrip(tmp_path):
+    from moge_b200.synthetic import save_checkpoint
+    cfg = model_config("vits", True)
+    path = tmp_path / "model.pt"
+    save_checkpoint(path, cfg, seed=0)
+    m = MoGeModel.from_pretrained(path).to(DEV).eval()
+    assert hasattr(m, "normal_head") and hasattr(m, "scale_head")
+    out = m.infer(synthetic_images(1, 70, 98, 3)[0].to(DEV), num_tokens=100)
+    torch.cuda.synchronize()
+    assert set(out.keys()) == {"points", "intrinsics", "depth", "mask", "normal"}
+    assert out["points"].shape == (70, 98, 3)
