@@ -1,0 +1,310 @@
+#!/usr/bin/env python
+"""Benchmark of the MoGe-2 hot path (BASELINE.json metric: images/sec, ViT-L, 518 px, fp16).
+
+  python bench.py --gpus 1 --steps K --warmup W                 engine arm (this repo, sm_100a kernels)
+  torchrun ... bench.py --gpus N ...                              one rank per GPU, weak scaling (fixed images per GPU)
+  python bench.py --impl reference ...                            the reference algorithm on the host cores (oracle port)
+
+A "step" is one `MoGeModel.infer()` over one batch of synthetic 518x518 images per GPU.  Rank 0 prints ONE JSON line.
+  value  : images/s with the inputs already resident in HBM (device-timed, max over ranks)
+  e2e    : images/s through the public API with HOST buffers: pinned host -> H2D -> infer -> D2H of every output
+  roofline      : encoder GEMM launches of the tcgen05 kernel (tensor bound), flops / CUDA-event time, live
+  roofline_decoder / roofline_attention : the other two kernel classes
+  cpu_baseline  : the oracle port (restated reference algorithm, fp32) timed on this box's host cores (rank 0, N=1)
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="engine", choices=["engine", "reference"])
+    ap.add_argument("--batch", type=int, default=32, help="images per GPU per step")
+    ap.add_argument("--size", default="vitl")
+    ap.add_argument("--res", type=int, default=518)
+    ap.add_argument("--tokens", type=int, default=1369, help="requested base tokens (1369 -> native 37x37 grid at 518 px)")
+    ap.add_argument("--dtype", default="fp16", choices=["fp16", "bf16"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-images", type=int, default=2)
+    return ap.parse_args()
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"hbm_gbs": d["hbm_gbs"], "tflops": d["bf16_tflops_sustained"], "source": "measured (MEASURED_PEAKS.json, sustained)"}
+    return {"hbm_gbs": 6650.0, "tflops": 1400.0, "source": "fallback (B200_PROFILING.md)"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons sampled every 200 ms while the timed region runs."""
+
+    def __init__(self, index):
+        self.index, self.rows, self.stop_flag, self.th = index, [], threading.Event(), None
+
+    def _run(self):
+        q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        while not self.stop_flag.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            self.stop_flag.wait(0.2)
+
+    def start(self):
+        self.th = threading.Thread(target=self._run, daemon=True)
+        self.th.start()
+
+    def stop(self):
+        self.stop_flag.set()
+        if self.th:
+            self.th.join(6)
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 7 for i in range(4) if r[3 + i].lower().startswith("active")})
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(self.rows)}
+
+
+def cpu_port_images_per_s(size, res, tokens, n_images, threads):
+    """The reference algorithm (oracle port, fp32) on the host cores: images/s over `n_images` single-image infers."""
+    from moge_b200.configs import model_config
+    from moge_b200.synthetic import make_state_dict, synthetic_images
+    from oracle import moge_port
+    torch.set_num_threads(threads)
+    cfg = model_config(size, True)
+    sd = make_state_dict(cfg, 0)
+    img = synthetic_images(1, res, res, 0)
+    moge_port.infer(cfg, sd, synthetic_images(1, 56, 56, 1), num_tokens=16)      # tiny warm-up (thread pool, allocator)
+    t0 = time.perf_counter()
+    for _ in range(n_images):
+        moge_port.infer(cfg, sd, img, num_tokens=tokens)
+    dt = time.perf_counter() - t0
+    return n_images / dt, dt
+
+
+def workload_name(a, h, w):
+    return (f"MoGe-2 {a.size} {a.dtype} infer(), {a.batch} x {a.res}x{a.res} images per GPU, num_tokens={a.tokens} -> {h}x{w} grid "
+            f"(BASELINE.json configs[1]/[3] shape; random-init weights)")
+
+
+def run_reference(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from moge_b200.configs import token_grid
+    threads = os.cpu_count() or 1
+    h, w = token_grid(a.res, a.res, a.tokens)
+    per_step = 1
+    for _ in range(max(a.warmup - 2, 0) if a.warmup > 2 else 0):
+        pass
+    # bounded sample: each step = 1 image; warm-up is capped at one image to keep the run within minutes
+    ips_w, _ = cpu_port_images_per_s(a.size, a.res, a.tokens, 1, threads) if a.warmup > 0 else (0, 0)
+    ips, dt = cpu_port_images_per_s(a.size, a.res, a.tokens, a.steps * per_step, threads)
+    line = {
+        "impl": "reference", "metric": "images/sec ViT-L 518px (MoGe-2 infer)", "value": ips, "unit": "images/s", "n_gpus": a.gpus,
+        "steps": a.steps, "warmup": min(a.warmup, 1), "ms_per_step": 1000.0 * dt / a.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(a, h, w), "sample": "1 image per step on the host cores"},
+        "cpu_baseline": {"value": ips, "unit": "images/s", "cores": threads, "kind": "port",
+                         "sample": f"{a.steps} single-image infer() calls, oracle/moge_port.py fp32, torch CPU {threads} threads"},
+        "e2e": {"value": ips, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def run_engine(a):
+    import torch.distributed as dist
+    from moge.model.v2 import MoGeModel
+    from moge_b200.configs import model_config, token_grid
+    from moge_b200.synthetic import make_state_dict
+    from moge_b200 import parallel
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    cfg = model_config(a.size, True)
+    # ---- weights: rank 0 builds the seeded checkpoint; one NCCL broadcast ships it to every GPU
+    t_w = time.perf_counter()
+    if world > 1:
+        sd = parallel.broadcast_state_dict(make_state_dict(cfg, 0) if rank == 0 else None, dev)
+    else:
+        sd = make_state_dict(cfg, 0)
+    model = MoGeModel(**cfg)
+    model.load_state_dict(sd)
+    model = model.to(dev).eval()
+    if a.dtype == "bf16":
+        model = model.bfloat16()
+    B, R = a.batch, a.res
+    h, w = token_grid(R, R, a.tokens)
+    g = torch.Generator().manual_seed(1234 + rank)
+    host_in = torch.rand(B, 3, R, R, generator=g).pin_memory()
+    dev_in = host_in.to(dev)
+    out = model.infer(dev_in, num_tokens=a.tokens)            # builds engine + plan
+    torch.cuda.synchronize()
+    del sd
+    load_s = time.perf_counter() - t_w
+    host_out = {k: torch.empty(v.shape, dtype=v.dtype).pin_memory() for k, v in out.items()}
+    d2h_bytes = sum(v.numel() * v.element_size() for v in out.values())
+    h2d_bytes = host_in.numel() * host_in.element_size()
+    n_ops = len(model.engine_ops()) + 2                        # + focal/shift solve + post-processing
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        barrier()
+        return float(ms.item())
+
+    def step_dev():
+        model.infer(dev_in, num_tokens=a.tokens)
+
+    def step_e2e():
+        x = host_in.to(dev, non_blocking=True)
+        o = model.infer(x, num_tokens=a.tokens)
+        for k, v in o.items():
+            host_out[k].copy_(v, non_blocking=True)
+
+    for _ in range(a.warmup):
+        step_dev()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ms_dev = timed(step_dev, a.steps)
+    clocks = sampler.stop() if rank == 0 else None
+    for _ in range(min(a.warmup, 2)):
+        step_e2e()
+    ms_e2e = timed(step_e2e, a.steps)
+
+    # ---- output gather to rank 0 over NCCL (config 4 of BASELINE.json), measured separately
+    gather = None
+    if world > 1:
+        o = model.infer(dev_in, num_tokens=a.tokens)
+        counts = [B] * world
+        ms_g = timed(lambda: parallel.gather_outputs(o, counts), 1)
+        gather = {"ms": ms_g, "bytes_to_rank0": d2h_bytes * (world - 1)}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    # ---- per-launch CUDA-event profile of one step -> roofline of each kernel class (live, same process)
+    model.infer(dev_in, num_tokens=a.tokens)
+    ops = model.engine_ops()
+    prof = [model.engine_profile() for _ in range(3)]
+    ms_op = [min(p[i] for p in prof) for i in range(len(ops))]
+    pk = peaks()
+
+    def cls(prefixes):
+        idx = [i for i, (n, _, _) in enumerate(ops) if n.startswith(prefixes)]
+        t = sum(ms_op[i] for i in idx) / 1e3
+        return idx, t, sum(ops[i][1] for i in idx), sum(ops[i][2] for i in idx)
+
+    total_prof_ms = sum(ms_op)
+    idx, t, fl, by = cls(("gemm.",))
+    roofline = {"kernel": "umma_kernel<AMODE_ROWS> (encoder linears: patch/qkv/proj/fc1/fc2/taps)", "bound": "tensor",
+                "achieved": fl / t / 1e12, "peak": pk["tflops"], "unit": "TFLOP/s", "frac": fl / t / 1e12 / pk["tflops"],
+                "traffic": None, "launches": len(idx), "ms_per_step": t * 1e3, "share_of_step": t * 1e3 / total_prof_ms,
+                "peak_source": pk["source"]}
+    idx, t, fl, by = cls(("conv", "upsample2x"))
+    dec_bound_s = max(fl / (pk["tflops"] * 1e12), by / (pk["hbm_gbs"] * 1e9))
+    roofline_decoder = {"kernel": "umma_kernel<AMODE_TILES> (implicit-GEMM convs) + upsample2x", "bound": "hbm",
+                        "achieved": by / t / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": by / t / 1e9 / pk["hbm_gbs"],
+                        "tensor_tflops": fl / t / 1e12, "frac_of_max_bound": dec_bound_s / t, "traffic": None, "launches": len(idx),
+                        "ms_per_step": t * 1e3, "share_of_step": t * 1e3 / total_prof_ms}
+    idx, t, fl, by = cls(("attention",))
+    roofline_attention = {"kernel": "attention_kernel", "bound": "tensor", "achieved": fl / t / 1e12, "peak": pk["tflops"],
+                          "unit": "TFLOP/s", "frac": fl / t / 1e12 / pk["tflops"], "launches": len(idx), "ms_per_step": t * 1e3,
+                          "share_of_step": t * 1e3 / total_prof_ms}
+    other_ms = total_prof_ms - roofline["ms_per_step"] - roofline_decoder["ms_per_step"] - roofline_attention["ms_per_step"]
+
+    # ---- batch-1 latency (BASELINE.json configs[1]): p50 over 30 device-timed single-image infers
+    one = dev_in[:1].contiguous()
+    for _ in range(5):
+        model.infer(one, num_tokens=a.tokens)
+    lat = []
+    for _ in range(30):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        model.infer(one, num_tokens=a.tokens)
+        e1.record()
+        torch.cuda.synchronize()
+        lat.append(e0.elapsed_time(e1))
+    latency = {"batch": 1, "p50_ms": statistics.median(lat), "p90_ms": sorted(lat)[int(0.9 * len(lat))], "iters": len(lat)}
+
+    cpu = None
+    if world == 1 and not a.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        ips, dt = cpu_port_images_per_s(a.size, R, a.tokens, a.cpu_images, threads)
+        cpu = {"value": ips, "unit": "images/s", "cores": threads, "kind": "port",
+               "sample": f"{a.cpu_images} single-image infer() calls ({dt:.1f} s), oracle/moge_port.py fp32, torch CPU {threads} threads"}
+
+    images = B * world * a.steps
+    line = {
+        "metric": "images/sec ViT-L 518px fp16 (MoGe-2 infer)", "value": images / (ms_dev / 1e3), "unit": "images/s", "n_gpus": world,
+        "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms_dev / a.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": a.dtype, "data": "synthetic",
+        "config": {"workload": workload_name(a, h, w), "images_per_gpu": B, "grid": [h, w],
+                   "l2": "per-step working set (activation workspace, GBs) far exceeds the 126 MB L2; no explicit flush",
+                   "weights": "seeded random init (moge_b200.synthetic), broadcast from rank 0 over NCCL" if world > 1 else "seeded random init"},
+        "e2e": {"value": images / (ms_e2e / 1e3), "unit": "images/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
+                "ms_per_step": ms_e2e / a.steps},
+        "gpu_launches": n_ops * a.steps,
+        "launches_per_step": n_ops,
+        "clocks": clocks,
+        "roofline": roofline, "roofline_decoder": roofline_decoder, "roofline_attention": roofline_attention,
+        "profile_ms": {"sum_of_launches": total_prof_ms, "other_kernels": other_ms},
+        "latency": latency,
+        "cpu_baseline": cpu,
+        "load_s": load_s,
+    }
+    if gather:
+        line["gather"] = gather
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_engine(args)

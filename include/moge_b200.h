@@ -86,6 +86,13 @@ int moge_engine_forward(moge_engine_t* e, const void* image, int image_dtype, in
                         void* workspace, size_t workspace_bytes, float* points, float* normal, float* mask_prob,
                         float* metric_scale, void* stream);
 
+/* ---- introspection of the launch list of the most recent forward (used by bench.py for the roofline numbers):
+ * number of kernel launches, per-launch kernel class / algorithmic flops / algorithmic HBM bytes, and a profiling
+ * replay that brackets every launch with CUDA events on `stream` (this one call synchronises the stream). */
+int moge_engine_num_ops(moge_engine_t* e, int* n);
+int moge_engine_op_info(moge_engine_t* e, int idx, char* name, int name_cap, double* flops, double* bytes);
+int moge_engine_profile(moge_engine_t* e, float* ms_per_op, int cap, void* stream);
+
 /* replaces recover_focal_shift (moge/utils/geometry_torch.py:115-170 + geometry_numpy.py:79-112; SciPy LM on the
  * host in the reference).  points (B,H,W,3) fp32.  Mask: mask_u8 (B,H,W) if non-NULL, else mask_prob > 0.5 if
  * non-NULL, else all valid.  focal_in: NULL (solve focal and shift) or (B,) known focal (solve shift only).      */

@@ -19,7 +19,7 @@ RESAMPLE = {"conv_transpose": 0, "bilinear": 1}
 
 EXPORTS = [
     "moge_last_error", "moge_version", "moge_engine_create", "moge_engine_destroy", "moge_engine_set_weight",
-    "moge_engine_finalize", "moge_engine_workspace_bytes", "moge_engine_forward", "moge_recover_focal_shift",
+    "moge_engine_finalize", "moge_engine_workspace_bytes", "moge_engine_forward", "moge_engine_num_ops", "moge_engine_op_info", "moge_engine_profile", "moge_recover_focal_shift",
     "moge_postprocess", "moge_op_linear", "moge_op_attention", "moge_op_layernorm", "moge_op_conv",
 ]
 
@@ -69,6 +69,9 @@ def lib() -> C.CDLL:
     L.moge_engine_finalize.argtypes = [vp, vp]
     L.moge_engine_workspace_bytes.argtypes = [vp, ci, ci, ci, ci, ci, C.POINTER(C.c_size_t)]
     L.moge_engine_forward.argtypes = [vp, vp, ci, ci, ci, ci, ci, ci, vp, C.c_size_t, cf, cf, cf, cf, vp]
+    L.moge_engine_num_ops.argtypes = [vp, C.POINTER(ci)]
+    L.moge_engine_op_info.argtypes = [vp, ci, C.c_char_p, ci, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    L.moge_engine_profile.argtypes = [vp, C.POINTER(C.c_float), ci, vp]
     L.moge_recover_focal_shift.argtypes = [vp, vp, vp, ci, ci, ci, vp, vp, vp, vp]
     L.moge_postprocess.argtypes = [vp, vp, vp, vp, vp, vp, ci, ci, ci, ci, ci, vp, vp, vp, vp, vp]
     L.moge_op_linear.argtypes = [vp, vp, vp, vp, vp, ci, ci, ci, ci, ci, vp]

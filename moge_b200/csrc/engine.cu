@@ -57,11 +57,25 @@ struct StackW {
     int ncomp = 0;
 };
 
+struct Op {
+    std::function<int(cudaStream_t)> fn;
+    std::string name;      // kernel class + role, e.g. "gemm.qkv", "conv3x3.neck.l2", "attention"
+    double flops = 0;      // algorithmic flops (2*MAC) of this launch
+    double bytes = 0;      // algorithmic HBM bytes of this launch (each operand/result once)
+};
+
+struct OpList : std::vector<Op> {
+    void add(std::function<int(cudaStream_t)> fn, const char* name, double flops = 0, double bytes = 0) {
+        Op o; o.fn = std::move(fn); o.name = name; o.flops = flops; o.bytes = bytes;
+        push_back(std::move(o));
+    }
+};
+
 struct Plan {
     int B, H, W, h, w;
     void* ws;
     size_t ws_bytes;
-    std::vector<std::function<int(cudaStream_t)>> ops;
+    OpList ops;
     float* pos_table = nullptr;   // engine-owned, [T, D]
     float* cls_row = nullptr;
     bool table_ready = false;
@@ -89,6 +103,7 @@ struct moge_engine {
     StackW neck, heads[3];            // heads: points, normal, mask
     std::vector<const float*> mlp_w, mlp_b;
     std::vector<std::unique_ptr<Plan>> plans;
+    Plan* last_plan = nullptr;
 
     int alloc(void** p, size_t bytes) {
         CUDA_TRY(cudaMalloc(p, bytes ? bytes : 16));
@@ -389,7 +404,7 @@ static size_t map_bytes(const Level& g, int B, int C) { return static_cast<size_
 // conv-type launch on padded NHWC maps. src/aux/skip/out buffers live in the workspace.
 static int add_conv(moge_engine* e, Plan* pl, const ConvW& cw, const void* src, const void* aux, const Level& gs, int B,
                     int epi, void* out_raw, void* out_relu, const void* skip, const Level& go, int out_ch, bool shuffle,
-                    bool uv, float su, float sv, int ncomp = 0, const float* waux = nullptr) {
+                    bool uv, float su, float sv, const char* name, int ncomp = 0, const float* waux = nullptr) {
     UmmaParams p{};
     p.N = cw.N; p.ntaps = cw.taps; p.kb_main = cw.cin / 64; p.kb_aux = cw.caux / 64;
     p.B = B; p.H = gs.H; p.W = gs.W;
@@ -412,12 +427,17 @@ static int add_conv(moge_engine* e, Plan* pl, const ConvW& cw, const void* src, 
     else mx = ma;
     MG_TRY(make_map_2d(&mb, cw.w, cw.Ktot, cw.N, cw.Ktot, bn));
     const bool bf16 = e->bf16; const int sms = e->num_sms;
-    pl->ops.push_back([=](cudaStream_t st) { return launch_umma(bn, AMODE_TILES, epi, bf16, ma, mx, mb, p, sms, st); });
+    const double px = static_cast<double>(B) * gs.H * gs.W;
+    const double flops = 2.0 * px * cw.N * cw.Ktot;
+    double bytes = px * cw.cin * 2 + px * cw.caux * 2 + static_cast<double>(cw.N) * cw.Ktot * 2;
+    if (epi == EPI_HEADOUT) bytes += px * 32 * 2 + px * (ncomp == 1 ? 4 : 16);
+    else bytes += px * cw.N * 2 * ((out_raw ? 1 : 0) + (out_relu ? 1 : 0)) + (skip ? px * cw.N * 2 : 0);
+    pl->ops.add([=](cudaStream_t st) { return launch_umma(bn, AMODE_TILES, epi, bf16, ma, mx, mb, p, sms, st); }, name, flops, bytes);
     return 0;
 }
 
 static int add_linear(moge_engine* e, Plan* pl, const void* A, int M, int K, int lda, const void* W, int N, int epi,
-                      void* out, const float* bias, const float* v1, int ldo, int T = 0, int gridw = 0) {
+                      void* out, const float* bias, const float* v1, int ldo, const char* name, int T = 0, int gridw = 0) {
     UmmaParams p{};
     p.M = M; p.N = N; p.ntaps = 1; p.kb_main = (K + 63) / 64; p.kb_aux = 0;
     p.num_m_tiles = (M + TILE_M - 1) / TILE_M;
@@ -429,7 +449,11 @@ static int add_linear(moge_engine* e, Plan* pl, const void* A, int M, int K, int
     MG_TRY(make_map_2d(&ma, A, K, M, lda, TILE_M));
     MG_TRY(make_map_2d(&mb, W, K, N, lda, bn));
     const bool bf16 = e->bf16; const int sms = e->num_sms;
-    pl->ops.push_back([=](cudaStream_t st) { return launch_umma(bn, AMODE_ROWS, epi, bf16, ma, ma, mb, p, sms, st); });
+    const double flops = 2.0 * M * static_cast<double>(N) * K;
+    double bytes = static_cast<double>(M) * K * 2 + static_cast<double>(N) * K * 2;
+    bytes += (epi == EPI_RESID) ? static_cast<double>(M) * N * 8 : (epi == EPI_PATCH) ? static_cast<double>(M) * N * 4 + static_cast<double>(T) * N * 4
+                                                                                      : static_cast<double>(M) * N * 2;
+    pl->ops.add([=](cudaStream_t st) { return launch_umma(bn, AMODE_ROWS, epi, bf16, ma, ma, mb, p, sms, st); }, name, flops, bytes);
     return 0;
 }
 
@@ -437,22 +461,27 @@ struct StackBufs {     // per-level scratch maps of one ConvStack
     std::vector<void*> x_raw, x_relu, y_relu, t_up;
 };
 
-static int plan_stack(moge_engine* e, Plan* pl, const moge_stack_config_t& sc, const StackW& sw, bool is_neck, int B, int h,
+static int plan_stack(moge_engine* e, Plan* pl, const char* sname, const moge_stack_config_t& sc, const StackW& sw, bool is_neck, int B, int h,
                       int w, float su, float sv, StackBufs& sb, const std::vector<void*>& neck_out, void* x0_raw, void* x0_relu,
                       void* lowres_out) {
     const int L = sc.num_levels;
     const int* C = sc.dim_res_blocks;
     void* x_raw = x0_raw;
     void* x_relu = x0_relu;
+    static std::vector<std::unique_ptr<std::string>> names;      // op names outlive the plan
+    auto nm = [&](const char* kind, int l) {
+        names.emplace_back(new std::string(std::string(kind) + "." + sname + ".l" + std::to_string(l)));
+        return names.back()->c_str();
+    };
     for (int l = 0; l < L; ++l) {
         const Level g = level_geom(h, w, l);
         const int nres = sc.num_res_blocks[l];
         for (int r = 0; r < nres; ++r) {
             // y = conv3(relu(x)) -> only relu(y) is ever consumed
-            MG_TRY(add_conv(e, pl, sw.res[l][2 * r], x_relu, nullptr, g, B, EPI_DEC, nullptr, sb.y_relu[l], nullptr, g, C[l], false, false, 0, 0));
+            MG_TRY(add_conv(e, pl, sw.res[l][2 * r], x_relu, nullptr, g, B, EPI_DEC, nullptr, sb.y_relu[l], nullptr, g, C[l], false, false, 0, 0, nm("conv3x3.res_a", l)));
             // x = x + conv3(relu(y))
             void* nraw = (x_raw == sb.x_raw[l]) ? sb.t_up[l] : sb.x_raw[l];     // ping-pong between two raw maps
-            MG_TRY(add_conv(e, pl, sw.res[l][2 * r + 1], sb.y_relu[l], nullptr, g, B, EPI_DEC, nraw, (r + 1 < nres) ? x_relu : nullptr, x_raw, g, C[l], false, false, 0, 0));
+            MG_TRY(add_conv(e, pl, sw.res[l][2 * r + 1], sb.y_relu[l], nullptr, g, B, EPI_DEC, nraw, (r + 1 < nres) ? x_relu : nullptr, x_raw, g, C[l], false, false, 0, 0, nm("conv3x3.res_b", l)));
             x_raw = nraw;
         }
         if (is_neck) const_cast<std::vector<void*>&>(neck_out)[l] = x_raw;
@@ -461,23 +490,24 @@ static int plan_stack(moge_engine* e, Plan* pl, const moge_stack_config_t& sc, c
         const bool tail = !is_neck && (l + 1 == L - 1);
         const void* conv_src;
         if (sc.resamplers[l] == MOGE_RESAMPLE_CONV_TRANSPOSE) {
-            MG_TRY(add_conv(e, pl, sw.convT[l], x_raw, nullptr, g, B, EPI_DEC, sb.t_up[l + 1], nullptr, nullptr, gn, C[l + 1], true, false, 0, 0));
+            MG_TRY(add_conv(e, pl, sw.convT[l], x_raw, nullptr, g, B, EPI_DEC, sb.t_up[l + 1], nullptr, nullptr, gn, C[l + 1], true, false, 0, 0, nm("convT", l)));
             conv_src = sb.t_up[l + 1];
         } else {
             void* up = sb.t_up[l + 1];
             const bool bf16 = e->bf16;
             const int Cl = C[l];
             void* src = x_raw;
-            pl->ops.push_back([=](cudaStream_t st) { return launch_upsample2x(src, up, B, g.H, g.W, g.Hp, g.Wp, gn.Hp, gn.Wp, Cl, bf16, st); });
+            pl->ops.add([=](cudaStream_t st) { return launch_upsample2x(src, up, B, g.H, g.W, g.Hp, g.Wp, gn.Hp, gn.Wp, Cl, bf16, st); },
+                        nm("upsample2x", l), 0, static_cast<double>(B) * g.H * g.W * Cl * 2 * 5);
             conv_src = up;
         }
         if (tail) {
-            MG_TRY(add_conv(e, pl, sw.headout, conv_src, nullptr, gn, B, EPI_HEADOUT, lowres_out, nullptr, neck_out[l + 1], gn, 0, false, false, 0, 0, sw.ncomp, sw.waux));
+            MG_TRY(add_conv(e, pl, sw.headout, conv_src, nullptr, gn, B, EPI_HEADOUT, lowres_out, nullptr, neck_out[l + 1], gn, 0, false, false, 0, 0, nm("conv3x3.headout", l + 1), sw.ncomp, sw.waux));
             break;
         }
         const bool need_relu = sc.num_res_blocks[l + 1] > 0;
         MG_TRY(add_conv(e, pl, sw.post[l], conv_src, is_neck ? nullptr : neck_out[l + 1], gn, B, EPI_DEC, sb.x_raw[l + 1],
-                        need_relu ? sb.x_relu[l + 1] : nullptr, nullptr, gn, C[l + 1], false, is_neck, su, sv));
+                        need_relu ? sb.x_relu[l + 1] : nullptr, nullptr, gn, C[l + 1], false, is_neck, su, sv, nm("conv3x3.post", l + 1)));
         x_raw = sb.x_raw[l + 1];
         x_relu = sb.x_relu[l + 1];
     }
@@ -538,34 +568,37 @@ static int build_plan(moge_engine* e, Plan* pl, bool dry, size_t* bytes_out) {
     const float su = aspect / sqrtf(1.f + aspect * aspect), sv = 1.f / sqrtf(1.f + aspect * aspect);
     Plan* P = pl;
     // ---- K1: resize + normalise + patchify (reads the image pointer bound at forward time)
-    pl->ops.push_back([=](cudaStream_t st) { return launch_preprocess(P->image, P->image_dtype, B, H, W, h, w, patches, 592, bf16, st); });
+    pl->ops.add([=](cudaStream_t st) { return launch_preprocess(P->image, P->image_dtype, B, H, W, h, w, patches, 592, bf16, st); },
+                "preprocess", 0, static_cast<double>(B) * 3 * H * W * 4 + static_cast<double>(B) * T * 592 * 2);
     // ---- K2/K3: patch embed + pos embed; cls rows
-    MG_TRY(add_linear(e, pl, patches, B * T, 592, 592, e->w_patch, D, EPI_PATCH, x, nullptr, pl->pos_table, D, T, w));
-    pl->ops.push_back([=](cudaStream_t st) { return launch_init_cls(x, P->cls_row, B, N, D, st); });
+    MG_TRY(add_linear(e, pl, patches, B * T, 592, 592, e->w_patch, D, EPI_PATCH, x, nullptr, pl->pos_table, D, "gemm.patch_embed", T, w));
+    pl->ops.add([=](cudaStream_t st) { return launch_init_cls(x, P->cls_row, B, N, D, st); }, "init_cls");
     // ---- transformer blocks
     int tap_idx = 0;
     for (int i = 0; i < c.depth; ++i) {
         const moge_engine::Blk& b = e->blk[i];
-        pl->ops.push_back([=](cudaStream_t st) { return launch_layernorm(x, b.ln1g, b.ln1b, ln, M, D, D, 0, 0, N, nullptr, bf16, st); });
-        MG_TRY(add_linear(e, pl, ln, M, D, D, b.wqkv, 3 * D, EPI_STORE16, qkv, b.bqkv, nullptr, 3 * D));
+        const double ln_bytes = static_cast<double>(M) * D * 6;
+        pl->ops.add([=](cudaStream_t st) { return launch_layernorm(x, b.ln1g, b.ln1b, ln, M, D, D, 0, 0, N, nullptr, bf16, st); }, "layernorm", 0, ln_bytes);
+        MG_TRY(add_linear(e, pl, ln, M, D, D, b.wqkv, 3 * D, EPI_STORE16, qkv, b.bqkv, nullptr, 3 * D, "gemm.qkv"));
         {
             CUtensorMap mq;
             MG_TRY(make_map_3d(&mq, qkv, 3 * D, N, B, 128));
             const int heads = c.num_heads;
-            pl->ops.push_back([=](cudaStream_t st) { return launch_attention(mq, att, B, N, D, heads, bf16, st); });
+            pl->ops.add([=](cudaStream_t st) { return launch_attention(mq, att, B, N, D, heads, bf16, st); }, "attention",
+                        4.0 * B * static_cast<double>(N) * N * D, static_cast<double>(M) * D * 8);
         }
-        MG_TRY(add_linear(e, pl, att, M, D, D, b.wproj, D, EPI_RESID, x, b.bproj, b.g1, D));
-        pl->ops.push_back([=](cudaStream_t st) { return launch_layernorm(x, b.ln2g, b.ln2b, ln, M, D, D, 0, 0, N, nullptr, bf16, st); });
-        MG_TRY(add_linear(e, pl, ln, M, D, D, b.wfc1, 4 * D, EPI_GELU16, hid, b.bfc1, nullptr, 4 * D));
-        MG_TRY(add_linear(e, pl, hid, M, 4 * D, 4 * D, b.wfc2, D, EPI_RESID, x, b.bfc2, b.g2, D));
+        MG_TRY(add_linear(e, pl, att, M, D, D, b.wproj, D, EPI_RESID, x, b.bproj, b.g1, D, "gemm.proj"));
+        pl->ops.add([=](cudaStream_t st) { return launch_layernorm(x, b.ln2g, b.ln2b, ln, M, D, D, 0, 0, N, nullptr, bf16, st); }, "layernorm", 0, ln_bytes);
+        MG_TRY(add_linear(e, pl, ln, M, D, D, b.wfc1, 4 * D, EPI_GELU16, hid, b.bfc1, nullptr, 4 * D, "gemm.fc1"));
+        MG_TRY(add_linear(e, pl, hid, M, 4 * D, 4 * D, b.wfc2, D, EPI_RESID, x, b.bfc2, b.g2, D, "gemm.fc2"));
         if (tap_idx < c.num_taps && c.taps[tap_idx] == i) {
             const int j = tap_idx++;
             const bool lasttap = (j == c.num_taps - 1);
             const int ld = c.num_taps * D;
             const float* ng = e->norm_g; const float* nbv = e->norm_b;
-            pl->ops.push_back([=](cudaStream_t st) {
+            pl->ops.add([=](cudaStream_t st) {
                 return launch_layernorm(x, ng, nbv, taps, M, D, ld, j * D, 1, N, lasttap ? cls : nullptr, bf16, st);
-            });
+            }, "layernorm.tap", 0, ln_bytes);
         }
     }
     if (tap_idx != c.num_taps) return set_error("intermediate_layers must be increasing block indices < depth");
@@ -575,10 +608,10 @@ static int build_plan(moge_engine* e, Plan* pl, bool dry, size_t* bytes_out) {
         std::vector<int> dims(c.scale_head_dims, c.scale_head_dims + c.scale_head_layers + 1);
         const int nl = c.scale_head_layers;
         for (int d : dims) if (d > 4096) return set_error("scale head width %d > 4096", d);
-        pl->ops.push_back([=](cudaStream_t st) {
+        pl->ops.add([=](cudaStream_t st) {
             if (!P->scale) return 0;
             return launch_scale_head(cls, mw.data(), mb.data(), dims.data(), nl, B, P->scale, mlp_scratch, st);
-        });
+        }, "scale_head");
     }
     // ---- neck level 0: folded projection GEMM over the concatenated taps (+UV rank-2 term) -> padded NHWC
     {
@@ -599,9 +632,10 @@ static int build_plan(moge_engine* e, Plan* pl, bool dry, size_t* bytes_out) {
         MG_TRY(make_map_2d(&ma, taps, f.Ktot, p.M, f.Ktot, TILE_M));
         MG_TRY(make_map_2d(&mb, f.w, f.Ktot, f.N, f.Ktot, bn));
         const int sms = e->num_sms;
-        pl->ops.push_back([=](cudaStream_t st) { return launch_umma(bn, AMODE_ROWS, EPI_DEC, bf16, ma, ma, mb, p, sms, st); });
+        pl->ops.add([=](cudaStream_t st) { return launch_umma(bn, AMODE_ROWS, EPI_DEC, bf16, ma, ma, mb, p, sms, st); }, "gemm.taps_proj",
+                    2.0 * p.M * static_cast<double>(f.N) * f.Ktot, static_cast<double>(p.M) * f.Ktot * 2 + static_cast<double>(f.N) * f.Ktot * 2 + static_cast<double>(p.M) * f.N * 2);
     }
-    MG_TRY(plan_stack(e, pl, c.neck, e->neck, true, B, h, w, su, sv, nb, neck_out, nb.x_raw[0], nb.x_relu[0], nullptr));
+    MG_TRY(plan_stack(e, pl, "neck", c.neck, e->neck, true, B, h, w, su, sv, nb, neck_out, nb.x_raw[0], nb.x_relu[0], nullptr));
     // ---- heads
     for (int i = 0; i < 3; ++i) {
         const moge_stack_config_t& sc = *head_cfg(e, i);
@@ -609,17 +643,17 @@ static int build_plan(moge_engine* e, Plan* pl, bool dry, size_t* bytes_out) {
         const Level g0 = level_geom(h, w, 0);
         const StackW& sw = e->heads[i];
         MG_TRY(add_conv(e, pl, sw.in0, neck_out[0], nullptr, g0, B, EPI_DEC, hb.x_raw[0], sc.num_res_blocks[0] > 0 ? hb.x_relu[0] : nullptr,
-                        nullptr, g0, sc.dim_res_blocks[0], false, false, 0, 0));
+                        nullptr, g0, sc.dim_res_blocks[0], false, false, 0, 0, i == 0 ? "conv1x1.points_head.l0" : i == 1 ? "conv1x1.normal_head.l0" : "conv1x1.mask_head.l0"));
         void* lowres = i == 0 ? static_cast<void*>(pts_lr) : i == 1 ? static_cast<void*>(nrm_lr) : static_cast<void*>(msk_lr);
-        MG_TRY(plan_stack(e, pl, sc, sw, false, B, h, w, su, sv, hb, neck_out, hb.x_raw[0], hb.x_relu[0], lowres));
+        MG_TRY(plan_stack(e, pl, head_name(i), sc, sw, false, B, h, w, su, sv, hb, neck_out, hb.x_raw[0], hb.x_relu[0], lowres));
     }
     // ---- K17 fused resize + remap
     {
         const int remap = c.remap_output;
-        pl->ops.push_back([=](cudaStream_t st) {
+        pl->ops.add([=](cudaStream_t st) {
             return launch_head_output(P->points ? pts_lr : nullptr, P->normal ? nrm_lr : nullptr, P->mask ? msk_lr : nullptr, B, gl.H, gl.W,
                                       H, W, remap, P->points, P->normal, P->mask, st);
-        });
+        }, "head_output", 0, static_cast<double>(B) * H * W * 28 + static_cast<double>(B) * gl.H * gl.W * 36);
     }
     return 0;
 }
@@ -630,7 +664,7 @@ static int get_plan(moge_engine* e, int B, int H, int W, int h, int w, void* ws,
             *out = p.get();
             return 0;
         }
-    if (e->plans.size() >= 16) e->plans.erase(e->plans.begin());
+    if (e->plans.size() >= 16) { if (e->last_plan == e->plans.front().get()) e->last_plan = nullptr; e->plans.erase(e->plans.begin()); }
     std::unique_ptr<Plan> pl(new Plan());
     pl->B = B; pl->H = H; pl->W = W; pl->h = h; pl->w = w; pl->ws = ws; pl->ws_bytes = ws_bytes;
     const int D = e->cfg.embed_dim;
@@ -745,7 +779,45 @@ int moge_engine_forward(moge_engine_t* e, const void* image, int image_dtype, in
     MG_TRY(get_plan(e, B, H, W, h, w, workspace, workspace_bytes, &pl, st));
     pl->image = image; pl->image_dtype = image_dtype;
     pl->points = points; pl->normal = normal; pl->mask = mask_prob; pl->scale = metric_scale;
-    for (auto& op : pl->ops) MG_TRY(op(st));
+    e->last_plan = pl;
+    for (auto& op : pl->ops) MG_TRY(op.fn(st));
+    return 0;
+}
+
+int moge_engine_num_ops(moge_engine_t* e, int* n) {
+    if (!e || !n) return set_error("null argument");
+    if (!e->last_plan) return set_error("no forward has run yet");
+    *n = static_cast<int>(e->last_plan->ops.size());
+    return 0;
+}
+
+int moge_engine_op_info(moge_engine_t* e, int idx, char* name, int name_cap, double* flops, double* bytes) {
+    if (!e || !e->last_plan) return set_error("no forward has run yet");
+    if (idx < 0 || idx >= static_cast<int>(e->last_plan->ops.size())) return set_error("op index %d out of range", idx);
+    const Op& op = e->last_plan->ops[idx];
+    if (name && name_cap > 0) snprintf(name, name_cap, "%s", op.name.c_str());
+    if (flops) *flops = op.flops;
+    if (bytes) *bytes = op.bytes;
+    return 0;
+}
+
+int moge_engine_profile(moge_engine_t* e, float* ms, int cap, void* stream) {
+    if (!e || !e->last_plan || !ms) return set_error("profile: run moge_engine_forward once first");
+    Plan* pl = e->last_plan;
+    const int n = static_cast<int>(pl->ops.size());
+    if (cap < n) return set_error("profile: need room for %d ops", n);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    CUDA_TRY(cudaSetDevice(e->device));
+    std::vector<cudaEvent_t> ev(n + 1);
+    for (auto& x : ev) CUDA_TRY(cudaEventCreate(&x));
+    CUDA_TRY(cudaEventRecord(ev[0], st));
+    for (int i = 0; i < n; ++i) {
+        MG_TRY(pl->ops[i].fn(st));
+        CUDA_TRY(cudaEventRecord(ev[i + 1], st));
+    }
+    CUDA_TRY(cudaStreamSynchronize(st));
+    for (int i = 0; i < n; ++i) CUDA_TRY(cudaEventElapsedTime(&ms[i], ev[i], ev[i + 1]));
+    for (auto& x : ev) cudaEventDestroy(x);
     return 0;
 }
 

@@ -256,6 +256,29 @@ class MoGeModel:
                 capi.current_stream()))
         return points, normal, mask, scale
 
+    def engine_ops(self):
+        """[(kernel name, algorithmic flops, algorithmic HBM bytes)] of the launch list of the most recent forward."""
+        L = capi.lib()
+        n = C.c_int()
+        capi.check(L.moge_engine_num_ops(self._engine, C.byref(n)))
+        out = []
+        buf = C.create_string_buffer(96)
+        fl, by = C.c_double(), C.c_double()
+        for i in range(n.value):
+            capi.check(L.moge_engine_op_info(self._engine, i, buf, 96, C.byref(fl), C.byref(by)))
+            out.append((buf.value.decode(), fl.value, by.value))
+        return out
+
+    def engine_profile(self):
+        """Replays the most recent forward with a CUDA-event pair around every launch; returns ms per launch."""
+        L = capi.lib()
+        n = C.c_int()
+        capi.check(L.moge_engine_num_ops(self._engine, C.byref(n)))
+        ms = (C.c_float * n.value)()
+        with torch.cuda.device(self._device):
+            capi.check(L.moge_engine_profile(self._engine, ms, n.value, capi.current_stream()))
+        return list(ms)
+
     # ------------------------------------------------------------------ public API
     def forward(self, image: torch.Tensor, num_tokens: Union[int, torch.LongTensor]) -> Dict[str, torch.Tensor]:
         if image.dim() != 4 or image.shape[1] != 3:

@@ -84,7 +84,7 @@ def _shapes(cfg: Dict) -> "OrderedDict[str, tuple]":
     return s
 
 
-def make_state_dict(cfg: Dict, seed: int = 0, mask_bias: float = 2.0) -> "OrderedDict[str, torch.Tensor]":
+def make_state_dict(cfg: Dict, seed: int = 0, mask_bias: float = 0.7) -> "OrderedDict[str, torch.Tensor]":
     """Seeded fp32 state dict with well-scaled values (activations O(1) through all layers).
 
     `mask_bias` shifts the mask head's output bias so that `mask > 0.5` holds for most pixels and the
@@ -118,8 +118,10 @@ def make_state_dict(cfg: Dict, seed: int = 0, mask_bias: float = 2.0) -> "Ordere
                 for d in shape[1:]:
                     fan_in *= d
             gain = 1.0
+            if name.split(".")[0] in ("neck", "points_head", "normal_head", "mask_head"):
+                gain = 0.9                     # keeps the signal alive through ~30 ReLU convs without blowing up
             if "output_blocks" in name:
-                gain = 0.5
+                gain = 0.3 if name.startswith("points_head") else 0.5     # log-depth logit within a few units
             t = randn(gain / fan_in ** 0.5)
         else:
             raise AssertionError(name)

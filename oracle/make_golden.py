@@ -57,6 +57,12 @@ def main():
         with torch.no_grad():
             fwd = ref.forward(img, nt)
             inf = ref.infer(img, num_tokens=tokens, use_fp16=False)
+            # the reference's OWN 16-bit deviation on these weights (CPU autocast), the yardstick for the engine's tolerance
+            dev16 = {}
+            for tag, dt_ in (("fp16", torch.float16), ("bf16", torch.bfloat16)):
+                with torch.autocast("cpu", dtype=dt_):
+                    f16 = ref.forward(img, nt)
+                dev16[tag] = {k: rel_l2(f16[k].float(), fwd[k]) for k in fwd}
         pf = moge_port.forward(cfg, sd, img, nt)
         pi = moge_port.infer(cfg, sd, img, num_tokens=tokens)
         report = {}
@@ -73,10 +79,12 @@ def main():
         report["inf.intrinsics"] = rel_l2(pi["intrinsics"], inf["intrinsics"])
         assert report["inf.intrinsics"] < 1e-4, (name, report)
         print(name, {k: f"{v:.2e}" for k, v in report.items()}, "mask_frac", float(m.float().mean()))
+        print("   reference autocast deviation:", {t: {k: f"{v:.1e}" for k, v in d.items()} for t, d in dev16.items()})
         sl = (slice(None), slice(None, None, stride), slice(None, None, stride))
         gold = {
             "meta": {"size": size, "with_normal": with_normal, "seed": seed, "shape": (B, H, W), "num_tokens": tokens,
-                     "stride": stride, "port_vs_reference": report},
+                     "stride": stride, "port_vs_reference": report,
+                     "reference_autocast_deviation": dev16},
             "forward": {k: (v[sl].contiguous() if v.dim() >= 3 else v) for k, v in fwd.items()},
             "infer": {k: (v[sl].contiguous() if v.dim() >= 3 and k != "intrinsics" else v) for k, v in inf.items()},
         }
