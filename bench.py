@@ -40,6 +40,7 @@ def parse():
     ap.add_argument("--dtype", default="fp16", choices=["fp16", "bf16"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-images", type=int, default=2)
+    ap.add_argument("--dump-ops", default=None, help="write the per-launch profile (name, ms, flops, bytes) to this JSON file")
     return ap.parse_args()
 
 
@@ -231,6 +232,9 @@ def run_engine(a):
     prof = [model.engine_profile() for _ in range(3)]
     ms_op = [min(p[i] for p in prof) for i in range(len(ops))]
     pk = peaks()
+    if a.dump_ops:
+        with open(a.dump_ops, "w") as fh:
+            json.dump([{"name": n, "ms": ms_op[i], "flops": f, "bytes": b} for i, (n, f, b) in enumerate(ops)], fh, indent=0)
 
     def cls(prefixes):
         idx = [i for i, (n, _, _) in enumerate(ops) if n.startswith(prefixes)]

@@ -465,23 +465,92 @@ focal_shift_kernel(const float* __restrict__ points, const float* __restrict__ m
         if (threadIdx.x == 0) { focal_out[b] = fixed ? focal_in[b] : 1.0f; shift_out[b] = 0.0f; }
         return;
     }
+    // ---- MINPACK lmdif restated for one unknown (what scipy.optimize.least_squares(method='lm', x0=0, ftol=1e-3,
+    // xtol=gtol=1e-8, x_scale=1 -> diag=1 (mode 2), factor=100) executes in the reference, geometry_numpy.py:90,109),
+    // with the analytic Jacobian in place of the forward difference.  Reproducing its trust-region updates and its
+    // ftol stopping rule -- not just its fixed point -- keeps parity with the reference on ill-posed maps as well.
+    const double ftol = 1e-3, xtol = 1e-8, gtol = 1e-8, epsmch = 2.220446049250313e-16, dwarf = 2.2250738585072014e-308;
     double s = 0.0;
     FsEval cur = fs_eval(s, x, y, z, u, v, valid, fixed, fgiven, red);
-    double lambda = 0.0;
-    for (int it = 0; it < 64; ++it) {
-        if (!(cur.jtj > 0.0)) break;
-        const double step = -cur.jtr / (cur.jtj * (1.0 + lambda));
-        const FsEval nxt = fs_eval(s + step, x, y, z, u, v, valid, fixed, fgiven, red);
-        if (nxt.cost <= cur.cost && isfinite(nxt.cost)) {
-            const bool done = fabs(step) <= 1e-9 * (fabs(s) + 1e-3) || (cur.cost - nxt.cost) <= 1e-14 * cur.cost;
-            s += step;
-            cur = nxt;
-            lambda = lambda * 0.25;
-            if (done) break;
-        } else {
-            lambda = (lambda == 0.0) ? 1.0 : lambda * 4.0;
-            if (lambda > 1e12) break;
+    double fnorm = sqrt(cur.cost);
+    double par = 0.0, delta = 0.0, xnorm = 0.0;
+    int nfev = 1;
+    bool stop = false;
+    for (int iter = 1; !stop && nfev < 200; ++iter) {
+        const double jtj = cur.jtj, jtr = cur.jtr;
+        const double jnorm = sqrt(jtj);
+        if (iter == 1) {
+            xnorm = fabs(s);
+            delta = 100.0 * xnorm;
+            if (delta == 0.0) delta = 100.0;
         }
+        double gnorm = 0.0;
+        if (fnorm != 0.0 && jnorm != 0.0) gnorm = fabs(jtr / jnorm) / fnorm;
+        if (gnorm <= gtol) break;                                   // info = 4
+        if (!(jnorm > 0.0) || !isfinite(jnorm)) break;
+        double ratio = 0.0;
+        do {
+            // ---- lmpar (n = 1, R = jnorm, Q^T f = jtr / jnorm): step xs solves (jtj + par) xs = jtr, p = -xs
+            const double qtb = jtr / jnorm;
+            double xs = qtb / jnorm;
+            double dxnorm = fabs(xs);
+            double fp = dxnorm - delta;
+            if (fp <= 0.1 * delta) {
+                par = 0.0;
+            } else {
+                double parl = (fp / delta) * jtj;
+                const double gn = fabs(jtr);
+                double paru = gn / delta;
+                if (paru == 0.0) paru = dwarf / fmin(delta, 0.1);
+                par = fmax(par, parl);
+                par = fmin(par, paru);
+                if (par == 0.0) par = gn / dxnorm;
+                for (int k = 1;; ++k) {
+                    if (par == 0.0) par = fmax(dwarf, 0.001 * paru);
+                    xs = jtr / (jtj + par);
+                    dxnorm = fabs(xs);
+                    const double temp = fp;
+                    fp = dxnorm - delta;
+                    if (fabs(fp) <= 0.1 * delta || (parl == 0.0 && fp <= temp && temp < 0.0) || k == 10) break;
+                    const double parc = (fp / delta) * (jtj + par);
+                    if (fp > 0.0) parl = fmax(parl, par);
+                    if (fp < 0.0) paru = fmin(paru, par);
+                    par = fmax(parl, par + parc);
+                }
+            }
+            const double pstep = -xs;
+            const double pnorm = fabs(pstep);
+            if (iter == 1) delta = fmin(delta, pnorm);
+            const FsEval nxt = fs_eval(s + pstep, x, y, z, u, v, valid, fixed, fgiven, red);
+            ++nfev;
+            const double fnorm1 = sqrt(nxt.cost);
+            double actred = -1.0;
+            if (0.1 * fnorm1 < fnorm) actred = 1.0 - (fnorm1 / fnorm) * (fnorm1 / fnorm);
+            const double temp1 = jnorm * pnorm / fnorm, temp2 = sqrt(par) * pnorm / fnorm;
+            const double prered = temp1 * temp1 + 2.0 * temp2 * temp2;
+            const double dirder = -(temp1 * temp1 + temp2 * temp2);
+            ratio = (prered != 0.0) ? actred / prered : 0.0;
+            if (ratio <= 0.25) {
+                double temp = (actred >= 0.0) ? 0.5 : 0.5 * dirder / (dirder + 0.5 * actred);
+                if (0.1 * fnorm1 >= fnorm || temp < 0.1) temp = 0.1;
+                delta = temp * fmin(delta, pnorm / 0.1);
+                par /= temp;
+            } else if (par == 0.0 || ratio >= 0.75) {
+                delta = pnorm / 0.5;
+                par *= 0.5;
+            }
+            if (ratio >= 1e-4) {                                    // successful iteration
+                s += pstep;
+                cur = nxt;
+                xnorm = fabs(s);
+                fnorm = fnorm1;
+            }
+            if (fabs(actred) <= ftol && prered <= ftol && 0.5 * ratio <= 1.0) stop = true;      // info = 1 (scipy status 2)
+            if (delta <= xtol * xnorm) stop = true;                                              // info = 2
+            if (fabs(actred) <= epsmch && prered <= epsmch && 0.5 * ratio <= 1.0) stop = true;  // info = 6
+            if (delta <= epsmch * xnorm) stop = true;                                            // info = 7
+            if (nfev >= 200 || !isfinite(fnorm1)) stop = true;
+        } while (!stop && ratio < 1e-4);
     }
     if (threadIdx.x == 0) {
         const float sf = static_cast<float>(s);                          // geometry_numpy.py:91 casts the shift to float32 ...

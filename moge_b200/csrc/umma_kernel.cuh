@@ -62,7 +62,8 @@ template <int BN> struct UmmaCfg {
     static constexpr int kEpiWarps = (BN >= 64) ? 8 : 4;
     static constexpr int kThreads = 64 + 32 * kEpiWarps;
     static constexpr int kTmemCols = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
-    static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+    static constexpr int kScratchBytes = kEpiWarps * 4096;   // per-epilogue-warp 32x32 fp32 transpose tile
+    static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/ + kScratchBytes;
     static constexpr int kColsPerWarp = (kEpiWarps == 8) ? BN / 2 : BN;
 };
 
@@ -81,6 +82,16 @@ __device__ __forceinline__ void store_px_border(uint8_t* base, int b, int Y, int
         }
 }
 
+// same for an 8-byte (4 x 16-bit) piece
+__device__ __forceinline__ void store_px_border8(uint8_t* base, int b, int Y, int X, int Ho, int Wo, int Hop, int Wop,
+                                                 int ld, int c0, uint2 q) {
+    const int y0 = (Y == 0) ? 0 : Y + 1, y1 = (Y == Ho - 1) ? Y + 2 : Y + 1;
+    const int x0 = (X == 0) ? 0 : X + 1, x1 = (X == Wo - 1) ? X + 2 : X + 1;
+    for (int yy = y0; yy <= y1; ++yy)
+        for (int xx = x0; xx <= x1; ++xx)
+            *reinterpret_cast<uint2*>(base + (((static_cast<size_t>(b) * Hop + yy) * Wop + xx) * ld + c0) * 2) = q;
+}
+
 template <int BN, int AMODE, int EPI, bool BF16>
 __global__ void __launch_bounds__(UmmaCfg<BN>::kThreads, 1)
 umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapAux,
@@ -95,6 +106,7 @@ umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
     uint64_t* tfull = empty + S;
     uint64_t* tempty = tfull + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+    float* scratch_base = reinterpret_cast<float*>(smem + S * Cfg::kStageBytes + 256);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -178,40 +190,33 @@ umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
         }
     } else {
         // ================================================================== epilogue
+        // TMEM hands each thread one accumulator ROW; global memory wants warps on contiguous COLUMNS.  Every 32x32
+        // chunk is therefore transposed through a per-warp swizzled smem tile: afterwards 8 lanes x float4 cover the
+        // 32 columns of one row and each warp instruction touches 4 rows (4 x 128 B), fully coalesced.
         const int ew = warp - 2;
         const int quarter = warp & 3;
         const int col_begin = (Cfg::kEpiWarps == 8) ? (ew >> 2) * (BN / 2) : 0;
         const int row = quarter * 32 + lane;
+        float4* scr = reinterpret_cast<float4*>(scratch_base + ew * 1024);
+        const int sub = lane >> 3;        // which of the 4 rows of a pass this lane serves
+        const int q4 = lane & 7;          // which float4 (4 columns) of the 32-column chunk
         int it = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
             const int mt = tile / p.num_n_tiles, nt = tile % p.num_n_tiles;
             const int acc = it & 1;
             const uint32_t aph = (it >> 1) & 1;
-            // ---- row -> output coordinates
-            bool valid;
-            long grow = 0;
-            int b = 0, py = 0, px = 0;
-            if (AMODE == AMODE_ROWS) {
-                grow = static_cast<long>(mt) * TILE_M + row;
-                valid = grow < p.M;
-                if (EPI == EPI_DEC || EPI == EPI_PATCH) {
-                    b = static_cast<int>(grow / p.T);
-                    const int t = static_cast<int>(grow % p.T);
-                    py = t / p.W; px = t % p.W;
-                }
-            } else {
-                const int per_img = p.tiles_x * p.tiles_y;
-                b = mt / per_img;
-                const int r = mt % per_img;
-                py = (r / p.tiles_x) * TILE_PH + row / TILE_PW;
-                px = (r % p.tiles_x) * TILE_PW + row % TILE_PW;
-                valid = (py < p.H) && (px < p.W);
-            }
             mbar_wait(&tfull[acc], aph);
             tc_fence_after();
             const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN + col_begin;
 
             if (EPI == EPI_HEADOUT) {
+                // lane = pixel: 16 B (or 4 B) per lane, consecutive lanes = consecutive pixels of a tile row
+                const int per_img = p.tiles_x * p.tiles_y;
+                const int b = mt / per_img;
+                const int r = mt % per_img;
+                const int py = (r / p.tiles_x) * TILE_PH + row / TILE_PW;
+                const int px = (r % p.tiles_x) * TILE_PW + row % TILE_PW;
+                const bool valid = (py < p.H) && (px < p.W);
                 float v[16];
                 tmem_ld16(t_addr, v);
                 tc_wait_ld();
@@ -237,105 +242,107 @@ umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
                     if (p.ncomp == 1) static_cast<float*>(p.out0)[pix] = o[0];
                     else static_cast<float4*>(p.out0)[pix] = make_float4(o[0], o[1], o[2], 0.f);
                 }
+                __syncwarp();
             } else {
+                // ---- coordinates of the 8 rows this lane serves after the transpose (row = 4*i + sub of the warp's 32)
+                bool ok[8];
+                int rb[8], ry[8], rx[8];
+                size_t roff[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int rl = quarter * 32 + 4 * i + sub;
+                    rb[i] = 0; ry[i] = 0; rx[i] = 0; roff[i] = 0;
+                    if (AMODE == AMODE_ROWS) {
+                        const long grow = static_cast<long>(mt) * TILE_M + rl;
+                        ok[i] = grow < p.M;
+                        roff[i] = static_cast<size_t>(grow) * p.ldo;
+                        if (EPI == EPI_DEC || EPI == EPI_PATCH) {
+                            rb[i] = static_cast<int>(grow / p.T);
+                            const int t = static_cast<int>(grow % p.T);
+                            ry[i] = t / p.W; rx[i] = t % p.W;
+                            if (EPI == EPI_PATCH) roff[i] = (static_cast<size_t>(rb[i]) * (p.T + 1) + 1 + t) * p.ldo;
+                        }
+                    } else {
+                        const int per_img = p.tiles_x * p.tiles_y;
+                        rb[i] = mt / per_img;
+                        const int r = mt % per_img;
+                        ry[i] = (r / p.tiles_x) * TILE_PH + rl / TILE_PW;
+                        rx[i] = (r % p.tiles_x) * TILE_PW + rl % TILE_PW;
+                        ok[i] = (ry[i] < p.H) && (rx[i] < p.W);
+                    }
+                }
 #pragma unroll 1
                 for (int c = 0; c < Cfg::kColsPerWarp; c += 32) {
                     float v[32];
                     tmem_ld32(t_addr + c, v);
                     tc_wait_ld();
+#pragma unroll
+                    for (int q = 0; q < 8; ++q)
+                        scr[lane * 8 + (q ^ (lane & 7))] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+                    __syncwarp();
                     const int col = nt * BN + col_begin + c;       // first global output column of this chunk
-                    if (!valid) {
-                        // nothing to store for padding rows (tcgen05.ld above stays warp-convergent)
-                    } else if (EPI == EPI_STORE16 || EPI == EPI_GELU16) {
-                        const float4* bp = reinterpret_cast<const float4*>(p.bias + col);
-                        uint4 q[4];
-                        uint32_t* qw = reinterpret_cast<uint32_t*>(q);
+                    int co = col + 4 * q4;                         // this lane's 4 columns
+                    int qd = 0;
+                    if (EPI == EPI_DEC && p.shuffle) {
+                        qd = col / p.ldo;                          // ldo == C_out; a 32-column chunk never straddles qd
+                        co -= qd * p.ldo;
+                    }
+                    float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f), g4 = bias4, h4 = bias4;
+                    if (EPI != EPI_PATCH) bias4 = *reinterpret_cast<const float4*>(p.bias + co);
+                    if (EPI == EPI_RESID) g4 = *reinterpret_cast<const float4*>(p.vec1 + co);
+                    if (EPI == EPI_DEC && p.vec1 != nullptr) {
+                        g4 = *reinterpret_cast<const float4*>(p.vec1 + co);
+                        h4 = *reinterpret_cast<const float4*>(p.vec2 + co);
+                    }
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            const float4 bb = bp[j];
-                            float a0 = v[4 * j] + bb.x, a1 = v[4 * j + 1] + bb.y, a2 = v[4 * j + 2] + bb.z, a3 = v[4 * j + 3] + bb.w;
-                            if (EPI == EPI_GELU16) { a0 = gelu_erf(a0); a1 = gelu_erf(a1); a2 = gelu_erf(a2); a3 = gelu_erf(a3); }
-                            qw[2 * j] = H::pack(a0, a1);
-                            qw[2 * j + 1] = H::pack(a2, a3);
-                        }
-                        uint4* dst = reinterpret_cast<uint4*>(static_cast<typename H::T*>(p.out0) + grow * p.ldo + col);
-                        dst[0] = q[0]; dst[1] = q[1]; dst[2] = q[2]; dst[3] = q[3];
-                    } else if (EPI == EPI_RESID) {
-                        const float4* bp = reinterpret_cast<const float4*>(p.bias + col);
-                        const float4* gp = reinterpret_cast<const float4*>(p.vec1 + col);
-                        float4* xp = reinterpret_cast<float4*>(static_cast<float*>(p.out0) + grow * p.ldo + col);
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            const float4 bb = bp[j], gg = gp[j];
-                            float4 x = xp[j];
-                            x.x += gg.x * (v[4 * j] + bb.x);
-                            x.y += gg.y * (v[4 * j + 1] + bb.y);
-                            x.z += gg.z * (v[4 * j + 2] + bb.z);
-                            x.w += gg.w * (v[4 * j + 3] + bb.w);
-                            xp[j] = x;
-                        }
-                    } else if (EPI == EPI_PATCH) {
-                        const int t = py * p.W + px;
-                        const float4* tp = reinterpret_cast<const float4*>(p.vec1 + static_cast<size_t>(t) * p.ldo + col);
-                        float4* xp = reinterpret_cast<float4*>(static_cast<float*>(p.out0) +
-                                                               (static_cast<size_t>(b) * (p.T + 1) + 1 + t) * p.ldo + col);
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            const float4 tt = tp[j];
-                            xp[j] = make_float4(v[4 * j] + tt.x, v[4 * j + 1] + tt.y, v[4 * j + 2] + tt.z, v[4 * j + 3] + tt.w);
-                        }
-                    } else if (EPI == EPI_DEC) {
-                        int Y = py, X = px, co = col;
-                        if (p.shuffle) {
-                            const int q = col / p.ldo;            // ldo == C_out; a 32-column chunk never straddles q
-                            co = col - q * p.ldo;
-                            Y = 2 * py + (q >> 1);
-                            X = 2 * px + (q & 1);
-                        }
-                        const float4* bp = reinterpret_cast<const float4*>(p.bias + co);
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            const float4 bb = bp[j];
-                            v[4 * j] += bb.x; v[4 * j + 1] += bb.y; v[4 * j + 2] += bb.z; v[4 * j + 3] += bb.w;
-                        }
-                        if (p.vec1 != nullptr) {
-                            const float uu = p.su * ((2 * X + 1) / static_cast<float>(p.Wo) - 1.0f);
-                            const float vv = p.sv * ((2 * Y + 1) / static_cast<float>(p.Ho) - 1.0f);
-                            const float4* up = reinterpret_cast<const float4*>(p.vec1 + co);
-                            const float4* vp = reinterpret_cast<const float4*>(p.vec2 + co);
-#pragma unroll
-                            for (int j = 0; j < 8; ++j) {
-                                const float4 a = up[j], d = vp[j];
-                                v[4 * j] += a.x * uu + d.x * vv; v[4 * j + 1] += a.y * uu + d.y * vv;
-                                v[4 * j + 2] += a.z * uu + d.z * vv; v[4 * j + 3] += a.w * uu + d.w * vv;
+                    for (int i = 0; i < 8; ++i) {
+                        const int rl = 4 * i + sub;
+                        float4 a = scr[rl * 8 + (q4 ^ (rl & 7))];
+                        if (!ok[i]) continue;
+                        if (EPI == EPI_STORE16 || EPI == EPI_GELU16) {
+                            a.x += bias4.x; a.y += bias4.y; a.z += bias4.z; a.w += bias4.w;
+                            if (EPI == EPI_GELU16) { a.x = gelu_erf(a.x); a.y = gelu_erf(a.y); a.z = gelu_erf(a.z); a.w = gelu_erf(a.w); }
+                            uint2 pk;
+                            pk.x = H::pack(a.x, a.y); pk.y = H::pack(a.z, a.w);
+                            *reinterpret_cast<uint2*>(static_cast<typename H::T*>(p.out0) + roff[i] + co) = pk;
+                        } else if (EPI == EPI_RESID) {
+                            float4* xp = reinterpret_cast<float4*>(static_cast<float*>(p.out0) + roff[i] + co);
+                            float4 x = *xp;
+                            x.x += g4.x * (a.x + bias4.x); x.y += g4.y * (a.y + bias4.y);
+                            x.z += g4.z * (a.z + bias4.z); x.w += g4.w * (a.w + bias4.w);
+                            *xp = x;
+                        } else if (EPI == EPI_PATCH) {
+                            const int t = ry[i] * p.W + rx[i];
+                            const float4 tt = *reinterpret_cast<const float4*>(p.vec1 + static_cast<size_t>(t) * p.ldo + co);
+                            *reinterpret_cast<float4*>(static_cast<float*>(p.out0) + roff[i] + co) =
+                                make_float4(a.x + tt.x, a.y + tt.y, a.z + tt.z, a.w + tt.w);
+                        } else if (EPI == EPI_DEC) {
+                            int Y = ry[i], X = rx[i];
+                            if (p.shuffle) { Y = 2 * Y + (qd >> 1); X = 2 * X + (qd & 1); }
+                            a.x += bias4.x; a.y += bias4.y; a.z += bias4.z; a.w += bias4.w;
+                            if (p.vec1 != nullptr) {
+                                const float uu = p.su * ((2 * X + 1) / static_cast<float>(p.Wo) - 1.0f);
+                                const float vv = p.sv * ((2 * Y + 1) / static_cast<float>(p.Ho) - 1.0f);
+                                a.x += g4.x * uu + h4.x * vv; a.y += g4.y * uu + h4.y * vv;
+                                a.z += g4.z * uu + h4.z * vv; a.w += g4.w * uu + h4.w * vv;
                             }
-                        }
-                        if (p.skip != nullptr) {
-                            const uint4* sp = reinterpret_cast<const uint4*>(
-                                static_cast<const uint8_t*>(p.skip) +
-                                (((static_cast<size_t>(b) * p.Hop + Y + 1) * p.Wop + X + 1) * p.ldo + co) * 2);
-#pragma unroll
-                            for (int j = 0; j < 4; ++j) {
-                                const uint4 u = sp[j];
-                                const uint32_t w[4] = {u.x, u.y, u.z, u.w};
-#pragma unroll
-                                for (int e = 0; e < 4; ++e) {
-                                    const float2 f = H::unpack(w[e]);
-                                    v[8 * j + 2 * e] += f.x; v[8 * j + 2 * e + 1] += f.y;
-                                }
+                            if (p.skip != nullptr) {
+                                const uint2 u = *reinterpret_cast<const uint2*>(
+                                    static_cast<const uint8_t*>(p.skip) +
+                                    (((static_cast<size_t>(rb[i]) * p.Hop + Y + 1) * p.Wop + X + 1) * p.ldo + co) * 2);
+                                const float2 f0 = H::unpack(u.x), f1 = H::unpack(u.y);
+                                a.x += f0.x; a.y += f0.y; a.z += f1.x; a.w += f1.y;
                             }
-                        }
-                        uint4 q[4];
-                        uint32_t* qw = reinterpret_cast<uint32_t*>(q);
-                        if (p.out0 != nullptr) {
-#pragma unroll
-                            for (int j = 0; j < 16; ++j) qw[j] = H::pack(v[2 * j], v[2 * j + 1]);
-                            store_px_border(static_cast<uint8_t*>(p.out0), b, Y, X, p.Ho, p.Wo, p.Hop, p.Wop, p.ldo, co, q);
-                        }
-                        if (p.out1 != nullptr) {
-#pragma unroll
-                            for (int j = 0; j < 16; ++j) qw[j] = H::pack(fmaxf(v[2 * j], 0.f), fmaxf(v[2 * j + 1], 0.f));
-                            store_px_border(static_cast<uint8_t*>(p.out1), b, Y, X, p.Ho, p.Wo, p.Hop, p.Wop, p.ldo, co, q);
+                            if (p.out0 != nullptr) {
+                                uint2 pk;
+                                pk.x = H::pack(a.x, a.y); pk.y = H::pack(a.z, a.w);
+                                store_px_border8(static_cast<uint8_t*>(p.out0), rb[i], Y, X, p.Ho, p.Wo, p.Hop, p.Wop, p.ldo, co, pk);
+                            }
+                            if (p.out1 != nullptr) {
+                                uint2 pk;
+                                pk.x = H::pack(fmaxf(a.x, 0.f), fmaxf(a.y, 0.f)); pk.y = H::pack(fmaxf(a.z, 0.f), fmaxf(a.w, 0.f));
+                                store_px_border8(static_cast<uint8_t*>(p.out1), rb[i], Y, X, p.Ho, p.Wo, p.Hop, p.Wop, p.ldo, co, pk);
+                            }
                         }
                     }
                     __syncwarp();

@@ -29,16 +29,17 @@ def test_focal_shift_matches_reference_golden(golden_dir):
     for i, c in enumerate(cases):
         pts, mask = synthetic_point_map(*c["args"][:7], seed=c["args"][7])
         f, s = _recover(pts, mask, c["focal_in"])
-        # tolerance: the reference stops its LM at ftol=1e-3; SURVEY.md 8c (2): |df|/f, |ds|/|s| <= 1e-4 on well-posed maps
-        assert torch.allclose(f, c["focal"], rtol=2e-4, atol=1e-6), (i, f, c["focal"])
-        assert torch.allclose(s, c["shift"], rtol=2e-4, atol=2e-5), (i, s, c["shift"])
+        # the kernel restates MINPACK lmdif (incl. its ftol=1e-3 early stop), so it lands on the reference's own iterate:
+        # 1e-5 relative (SURVEY.md 8c (2) allowed 1e-4 for a merely converged solver)
+        assert torch.allclose(f, c["focal"], rtol=1e-5, atol=1e-6), (i, f, c["focal"])
+        assert torch.allclose(s, c["shift"], rtol=1e-5, atol=1e-6), (i, s, c["shift"])
 
 
 def test_focal_shift_recovers_ground_truth():
     pts, mask = synthetic_point_map(3, 200, 300, 1.25, 0.4, 0.0, "all", seed=3)
     f, s = _recover(pts, mask)
-    assert torch.allclose(f, torch.full((3,), 1.25), rtol=1e-4)
-    assert torch.allclose(s, torch.full((3,), 0.4), rtol=1e-3, atol=1e-4)
+    assert torch.allclose(f, torch.full((3,), 1.25), rtol=1e-3)         # LM stops at ftol=1e-3 like the reference
+    assert torch.allclose(s, torch.full((3,), 0.4), rtol=3e-3, atol=1e-3)
 
 
 @pytest.mark.parametrize("force_projection,apply_mask", [(True, True), (False, True), (True, False)])
