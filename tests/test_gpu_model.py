@@ -133,8 +133,8 @@ def test_postprocess_chain_on_reference_forward_outputs(golden_dir):
         m = ginf["mask"]
         assert torch.equal(mout.cpu().bool(), m), name
         assert rel_l2(K, ginf["intrinsics"]) < 1e-5, name
-        assert rel_l2(pts.cpu()[m], ginf["points"][m]) < 1e-5, name
-        assert rel_l2(depth.cpu()[m], ginf["depth"][m]) < 1e-5, name
+        assert rel_l2(pts.cpu()[m], ginf["points"][m]) < 1e-4, name          # <= 1e-4 on the mask
+        assert rel_l2(depth.cpu()[m], ginf["depth"][m]) < 1e-4, name
         if nrm is not None:
             assert rel_l2(nout.cpu(), ginf["normal"]) < 1e-6, name
 
