@@ -1,6 +1,8 @@
 // Multi-head self-attention of the DINOv2 blocks (reference: dinov2/layers/attention.py:70-81, SDPA with
 // scale hd^-0.5, no mask) as one tcgen05 kernel: S = Q K^T and O~ = P V on the tensor cores with TMEM accumulators,
-// online softmax in registers, two 128-row query tiles per CTA ping-ponging on the tensor pipe.
+// single-pass online softmax in registers (the whole 128-wide score row lives in registers; FMNMX3 + MUFU.EX2),
+// O accumulated in TMEM by the MMA itself and rescaled lazily (only when the running max grows by more than 2^8),
+// two 128-row query tiles per CTA ping-ponging on the tensor pipe.
 //
 // Layout: qkv is the QKV-GEMM output [B, N, 3*D] (16-bit); Q/K/V tiles of head h are the column windows
 // [h*64, D+h*64, 2D+h*64) fetched by TMA straight from that buffer (no head-major repack): Q and K tiles are
@@ -16,7 +18,7 @@ constexpr int ATT_BQ = 128;       // query rows per softmax warpgroup
 constexpr int ATT_BKV = 128;      // keys per tile
 constexpr int ATT_KV_STAGES = 3;
 constexpr int ATT_TILE_BYTES = 128 * 128;   // [128 rows][64 x 16-bit]
-constexpr int ATT_THREADS = 64 + 256;
+constexpr int ATT_THREADS = 128 + 256;   // warpgroup 0: TMA warp, MMA warp, 2 idle; warpgroups 1,2: softmax
 // smem: Q0,Q1 | K[3] | V[3] | P0 (2 atoms) | P1 (2 atoms) | barriers
 constexpr int ATT_SMEM = (2 + 2 * ATT_KV_STAGES + 4) * ATT_TILE_BYTES + 1024 + 256;
 
@@ -44,8 +46,8 @@ attention_kernel(const __grid_constant__ CUtensorMap mapQKV, const AttnParams p)
     uint64_t* v_empty = bars + 10;           // 3
     uint64_t* s_full = bars + 13;            // 2
     uint64_t* p_full = bars + 15;            // 2
-    uint64_t* o_full = bars + 17;            // 2 groups x 2 buffers
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 21);
+    uint64_t* o_full = bars + 17;            // 2 (one per group; completes once per kv tile)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 19);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int q0 = blockIdx.x * 2 * ATT_BQ;
@@ -61,7 +63,7 @@ attention_kernel(const __grid_constant__ CUtensorMap mapQKV, const AttnParams p)
         }
         for (int g = 0; g < 2; ++g) {
             mbar_init(&s_full[g], 1); mbar_init(&p_full[g], 4);
-            mbar_init(&o_full[2 * g], 1); mbar_init(&o_full[2 * g + 1], 1);
+            mbar_init(&o_full[g], 1);
         }
         fence_mbar_init();
     }
@@ -70,9 +72,11 @@ attention_kernel(const __grid_constant__ CUtensorMap mapQKV, const AttnParams p)
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
-    // TMEM columns: S0 [0,128) S1 [128,256) O0 buffers [256,320),[320,384)  O1 buffers [384,448),[448,512)
+    // TMEM columns: S0 [0,128)  S1 [128,256)  O0 [256,320)  O1 [320,384)
 
+    // register re-balancing between the control warpgroup and the two softmax warpgroups (row of 128 scores in registers)
     if (warp == 0) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
         if (lane == 0) {
             mbar_arrive_expect_tx(q_full, 2 * ATT_TILE_BYTES);
             tma_load_3d(sQ, &mapQKV, q_full, h * ATT_HD, q0, b);
@@ -89,6 +93,7 @@ attention_kernel(const __grid_constant__ CUtensorMap mapQKV, const AttnParams p)
             }
         }
     } else if (warp == 1) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
         if (lane == 0) {
             constexpr uint32_t idesc_s = make_idesc(128, ATT_BKV, BF16 ? 1u : 0u, 0, 0);   // Q (K-major) x K (K-major)
             constexpr uint32_t idesc_o = make_idesc(128, ATT_HD, BF16 ? 1u : 0u, 0, 1);    // P (K-major) x V (MN-major)
@@ -102,16 +107,16 @@ attention_kernel(const __grid_constant__ CUtensorMap mapQKV, const AttnParams p)
             auto issue_pv = [&](int g, int j) {
                 const uint32_t pa = smem_u32(sP + g * 2 * ATT_TILE_BYTES);
                 const uint32_t va = smem_u32(sV + (j % ATT_KV_STAGES) * ATT_TILE_BYTES);
-                const uint32_t d = tmem + 256 + g * 128 + (j & 1) * 64;
+                const uint32_t d = tmem + 256 + g * 64;
 #pragma unroll
                 for (int k = 0; k < ATT_BKV / 16; ++k) {
                     // A: P, K-major; 4 K-steps per 64-column swizzle atom (atoms 16 KB apart)
                     const uint64_t a = make_sdesc_sw128(pa + (k >> 2) * ATT_TILE_BYTES) + 2 * (k & 3);
                     // B: V tile [kv][hd]: MN-major, 16 kv rows (= 2 groups of 8 x 128 B) per K-step
                     const uint64_t bd = make_sdesc_sw128(va + k * 16 * 128, /*lbo=*/ATT_TILE_BYTES, /*sbo=*/1024);
-                    umma_f16(d, a, bd, idesc_o, k != 0);
+                    umma_f16(d, a, bd, idesc_o, (j | k) != 0);       // O accumulates across kv tiles in TMEM
                 }
-                umma_commit(&o_full[2 * g + (j & 1)]);
+                umma_commit(&o_full[g]);
             };
             mbar_wait(q_full, 0);
             mbar_wait(&k_full[0], 0);
@@ -135,62 +140,71 @@ attention_kernel(const __grid_constant__ CUtensorMap mapQKV, const AttnParams p)
                 }
             }
         }
+    } else if (warp < 4) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
     } else {
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
         // ========================================================== softmax / accumulate / store (one row per thread)
-        const int g = (warp - 2) >> 2;
+        const int g = (warp - 4) >> 2;
         const int quarter = warp & 3;
         const int row = quarter * 32 + lane;
         const int qrow = q0 + g * ATT_BQ + row;
         const uint32_t lane_sel = static_cast<uint32_t>(quarter * 32) << 16;
         const uint32_t tS = tmem + lane_sel + g * 128;
-        const uint32_t tO = tmem + lane_sel + 256 + g * 128;
+        const uint32_t tO = tmem + lane_sel + 256 + g * 64;
         uint8_t* myP = sP + g * 2 * ATT_TILE_BYTES + (row >> 3) * 1024 + (row & 7) * 128;
         const int sw = row & 7;
-        float o[ATT_HD];
-#pragma unroll
-        for (int i = 0; i < ATT_HD; ++i) o[i] = 0.f;
-        float m = -INFINITY, l = 0.f;
+        float m = -INFINITY;            // reference max of the exponent (may lag the true running max by < 2^8)
+        float l = 0.f;
         const float sc = p.scale_log2;
         for (int j = 0; j < nkv; ++j) {
             mbar_wait(&s_full[g], j & 1);
             tc_fence_after();
-            const int kv_left = p.N - j * ATT_BKV;       // columns >= kv_left are padding
-            float mx = -INFINITY;
-#pragma unroll 1
-            for (int c = 0; c < ATT_BKV; c += 32) {
-                float v[32];
-                tmem_ld32(tS + c, v);
-                tc_wait_ld();
+            float v[ATT_BKV];
 #pragma unroll
-                for (int i = 0; i < 32; ++i) mx = fmaxf(mx, (c + i < kv_left) ? v[i] : -INFINITY);
+            for (int c = 0; c < ATT_BKV; c += 32) tmem_ld32(tS + c, v + c);
+            tc_wait_ld();
+            const int kv_left = p.N - j * ATT_BKV;
+            if (kv_left < ATT_BKV) {                    // only the last tile has padding columns
+#pragma unroll
+                for (int i = 0; i < ATT_BKV; ++i) v[i] = (i < kv_left) ? v[i] : -INFINITY;
             }
+            float mx = fmax3(v[0], v[1], v[2]);
+#pragma unroll
+            for (int i = 3; i + 1 < ATT_BKV; i += 2) mx = fmax3(mx, v[i], v[i + 1]);
+            mx = fmaxf(mx, v[ATT_BKV - 1]);
             const float m_new = fmaxf(m, mx);
-            const float alpha = exp2f((m - m_new) * sc);
+            const bool grow = (m_new - m) * sc > 8.0f;        // true on the first tile (m = -inf)
             if (j > 0) {
-                mbar_wait(&o_full[2 * g + ((j - 1) & 1)], ((j - 1) >> 1) & 1);
+                // PV(j-1) must have finished before P is overwritten (and before O is touched)
+                mbar_wait(&o_full[g], (j - 1) & 1);
                 tc_fence_after();
+                if (__any_sync(0xffffffffu, grow)) {
+                    const float alpha = grow ? ex2_approx((m - m_new) * sc) : 1.0f;
 #pragma unroll
-                for (int c = 0; c < ATT_HD; c += 32) {
-                    float v[32];
-                    tmem_ld32(tO + ((j - 1) & 1) * 64 + c, v);
-                    tc_wait_ld();
+                    for (int c = 0; c < ATT_HD; c += 32) {
+                        float o[32];
+                        tmem_ld32(tO + c, o);
+                        tc_wait_ld();
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) o[c + i] = (o[c + i] + v[i]) * alpha;
+                        for (int i = 0; i < 32; ++i) o[i] *= alpha;
+                        tmem_st32(tO + c, o);
+                    }
+                    tc_wait_st();
+                    l *= alpha;
                 }
             }
-            l *= alpha;
-            const float mb = m_new * sc;
-#pragma unroll 1
+            if (grow) m = m_new;
+            const float mb = m * sc;
+            float lsum = 0.f;
+#pragma unroll
             for (int c = 0; c < ATT_BKV; c += 32) {
-                float v[32];
-                tmem_ld32(tS + c, v);
-                tc_wait_ld();
                 uint32_t w[16];
 #pragma unroll
                 for (int i = 0; i < 32; i += 2) {
-                    const float p0 = (c + i < kv_left) ? exp2f(v[i] * sc - mb) : 0.f;
-                    const float p1 = (c + i + 1 < kv_left) ? exp2f(v[i + 1] * sc - mb) : 0.f;
-                    l += p0 + p1;
+                    const float p0 = ex2_approx(fmaf(v[c + i], sc, -mb));
+                    const float p1 = ex2_approx(fmaf(v[c + i + 1], sc, -mb));
+                    lsum += p0 + p1;
                     w[i >> 1] = H::pack(p0, p1);
                 }
                 uint8_t* atom = myP + (c >> 6) * ATT_TILE_BYTES;
@@ -200,25 +214,25 @@ attention_kernel(const __grid_constant__ CUtensorMap mapQKV, const AttnParams p)
                     *reinterpret_cast<uint4*>(atom + (((chunk0 + q) ^ sw) << 4)) =
                         make_uint4(w[4 * q], w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]);
             }
-            m = m_new;
+            l += lsum;
             fence_proxy_async_smem();
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&p_full[g]);
         }
-        mbar_wait(&o_full[2 * g + ((nkv - 1) & 1)], ((nkv - 1) >> 1) & 1);
+        mbar_wait(&o_full[g], (nkv - 1) & 1);
         tc_fence_after();
         const float inv = 1.0f / l;
 #pragma unroll
         for (int c = 0; c < ATT_HD; c += 32) {
-            float v[32];
-            tmem_ld32(tO + ((nkv - 1) & 1) * 64 + c, v);
+            float o[32];
+            tmem_ld32(tO + c, o);
             tc_wait_ld();
             if (qrow < p.N) {
                 uint4 q[4];
                 uint32_t* qw = reinterpret_cast<uint32_t*>(q);
 #pragma unroll
-                for (int i = 0; i < 32; i += 2) qw[i >> 1] = H::pack((o[c + i] + v[i]) * inv, (o[c + i + 1] + v[i + 1]) * inv);
+                for (int i = 0; i < 32; i += 2) qw[i >> 1] = H::pack(o[i] * inv, o[i + 1] * inv);
                 uint4* dst = reinterpret_cast<uint4*>(static_cast<typename H::T*>(p.out) +
                                                       (static_cast<size_t>(b) * p.N + qrow) * p.D + h * ATT_HD + c);
                 dst[0] = q[0]; dst[1] = q[1]; dst[2] = q[2]; dst[3] = q[3];

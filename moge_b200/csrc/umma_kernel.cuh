@@ -85,11 +85,15 @@ __device__ __forceinline__ void store_px_border(uint8_t* base, int b, int Y, int
 // same for an 8-byte (4 x 16-bit) piece
 __device__ __forceinline__ void store_px_border8(uint8_t* base, int b, int Y, int X, int Ho, int Wo, int Hop, int Wop,
                                                  int ld, int c0, uint2 q) {
-    const int y0 = (Y == 0) ? 0 : Y + 1, y1 = (Y == Ho - 1) ? Y + 2 : Y + 1;
-    const int x0 = (X == 0) ? 0 : X + 1, x1 = (X == Wo - 1) ? X + 2 : X + 1;
-    for (int yy = y0; yy <= y1; ++yy)
-        for (int xx = x0; xx <= x1; ++xx)
-            *reinterpret_cast<uint2*>(base + (((static_cast<size_t>(b) * Hop + yy) * Wop + xx) * ld + c0) * 2) = q;
+    uint8_t* centre = base + (((static_cast<size_t>(b) * Hop + Y + 1) * Wop + X + 1) * ld + c0) * 2;
+    *reinterpret_cast<uint2*>(centre) = q;
+    if (Y != 0 && Y != Ho - 1 && X != 0 && X != Wo - 1) return;      // interior pixel: done
+    const int dy0 = (Y == 0) ? -1 : 0, dy1 = (Y == Ho - 1) ? 1 : 0;
+    const int dx0 = (X == 0) ? -1 : 0, dx1 = (X == Wo - 1) ? 1 : 0;
+    const ptrdiff_t rowp = static_cast<ptrdiff_t>(Wop) * ld * 2, colp = static_cast<ptrdiff_t>(ld) * 2;
+    for (int dy = dy0; dy <= dy1; ++dy)
+        for (int dx = dx0; dx <= dx1; ++dx)
+            if (dy != 0 || dx != 0) *reinterpret_cast<uint2*>(centre + dy * rowp + dx * colp) = q;
 }
 
 template <int BN, int AMODE, int EPI, bool BF16>
@@ -294,6 +298,30 @@ umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
                         g4 = *reinterpret_cast<const float4*>(p.vec1 + co);
                         h4 = *reinterpret_cast<const float4*>(p.vec2 + co);
                     }
+                    // ---- phase 1: issue every global READ of this chunk (residual / pos table / skip) back to back, so
+                    //      their L2 latencies overlap instead of serialising behind the stores of the previous row
+                    float4 pre[8];
+                    int sY[8], sX[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        pre[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        sY[i] = ry[i]; sX[i] = rx[i];
+                        if (EPI == EPI_DEC && p.shuffle) { sY[i] = 2 * ry[i] + (qd >> 1); sX[i] = 2 * rx[i] + (qd & 1); }
+                        if (!ok[i]) continue;
+                        if (EPI == EPI_RESID) {
+                            pre[i] = *reinterpret_cast<const float4*>(static_cast<const float*>(p.out0) + roff[i] + co);
+                        } else if (EPI == EPI_PATCH) {
+                            const int t = ry[i] * p.W + rx[i];
+                            pre[i] = *reinterpret_cast<const float4*>(p.vec1 + static_cast<size_t>(t) * p.ldo + co);
+                        } else if (EPI == EPI_DEC && p.skip != nullptr) {
+                            const uint2 u = *reinterpret_cast<const uint2*>(
+                                static_cast<const uint8_t*>(p.skip) +
+                                (((static_cast<size_t>(rb[i]) * p.Hop + sY[i] + 1) * p.Wop + sX[i] + 1) * p.ldo + co) * 2);
+                            const float2 f0 = H::unpack(u.x), f1 = H::unpack(u.y);
+                            pre[i] = make_float4(f0.x, f0.y, f1.x, f1.y);
+                        }
+                    }
+                    // ---- phase 2: math + stores
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
                         const int rl = 4 * i + sub;
@@ -306,32 +334,21 @@ umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
                             pk.x = H::pack(a.x, a.y); pk.y = H::pack(a.z, a.w);
                             *reinterpret_cast<uint2*>(static_cast<typename H::T*>(p.out0) + roff[i] + co) = pk;
                         } else if (EPI == EPI_RESID) {
-                            float4* xp = reinterpret_cast<float4*>(static_cast<float*>(p.out0) + roff[i] + co);
-                            float4 x = *xp;
+                            float4 x = pre[i];
                             x.x += g4.x * (a.x + bias4.x); x.y += g4.y * (a.y + bias4.y);
                             x.z += g4.z * (a.z + bias4.z); x.w += g4.w * (a.w + bias4.w);
-                            *xp = x;
+                            *reinterpret_cast<float4*>(static_cast<float*>(p.out0) + roff[i] + co) = x;
                         } else if (EPI == EPI_PATCH) {
-                            const int t = ry[i] * p.W + rx[i];
-                            const float4 tt = *reinterpret_cast<const float4*>(p.vec1 + static_cast<size_t>(t) * p.ldo + co);
                             *reinterpret_cast<float4*>(static_cast<float*>(p.out0) + roff[i] + co) =
-                                make_float4(a.x + tt.x, a.y + tt.y, a.z + tt.z, a.w + tt.w);
+                                make_float4(a.x + pre[i].x, a.y + pre[i].y, a.z + pre[i].z, a.w + pre[i].w);
                         } else if (EPI == EPI_DEC) {
-                            int Y = ry[i], X = rx[i];
-                            if (p.shuffle) { Y = 2 * Y + (qd >> 1); X = 2 * X + (qd & 1); }
-                            a.x += bias4.x; a.y += bias4.y; a.z += bias4.z; a.w += bias4.w;
+                            const int Y = sY[i], X = sX[i];
+                            a.x += bias4.x + pre[i].x; a.y += bias4.y + pre[i].y; a.z += bias4.z + pre[i].z; a.w += bias4.w + pre[i].w;
                             if (p.vec1 != nullptr) {
                                 const float uu = p.su * ((2 * X + 1) / static_cast<float>(p.Wo) - 1.0f);
                                 const float vv = p.sv * ((2 * Y + 1) / static_cast<float>(p.Ho) - 1.0f);
                                 a.x += g4.x * uu + h4.x * vv; a.y += g4.y * uu + h4.y * vv;
                                 a.z += g4.z * uu + h4.z * vv; a.w += g4.w * uu + h4.w * vv;
-                            }
-                            if (p.skip != nullptr) {
-                                const uint2 u = *reinterpret_cast<const uint2*>(
-                                    static_cast<const uint8_t*>(p.skip) +
-                                    (((static_cast<size_t>(rb[i]) * p.Hop + Y + 1) * p.Wop + X + 1) * p.ldo + co) * 2);
-                                const float2 f0 = H::unpack(u.x), f1 = H::unpack(u.y);
-                                a.x += f0.x; a.y += f0.y; a.z += f1.x; a.w += f1.y;
                             }
                             if (p.out0 != nullptr) {
                                 uint2 pk;
