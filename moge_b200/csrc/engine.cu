@@ -165,16 +165,25 @@ static int sum_bias(moge_engine* e, const float* a, const float* b, int n, float
 
 // 3x3 conv (Cout,Cin,3,3) [+ aux 1x1 (Cout,Caux,1,1)] [+ UV 1x1 (Cout,2,1,1)] -> ConvW
 static int pack_conv3(moge_engine* e, const std::string& wkey, int Cout, int Cin, const std::string& in_key, int Caux,
-                      bool uv, ConvW* cw, cudaStream_t st) {
+                      bool uv, ConvW* cw, cudaStream_t st, bool up2 = false) {
     const RawWeight* w;
     MG_TRY(get_raw(e, wkey + ".weight", &w, {Cout, Cin, 3, 3}));
     const float* b;
     MG_TRY(vec(e, wkey + ".bias", Cout, &b));
     if (Cin % 64) return set_error("conv '%s': C_in=%d must be a multiple of 64", wkey.c_str(), Cin);
-    cw->N = Cout; cw->cin = Cin; cw->caux = Caux; cw->taps = 9;
+    const float* wsrc = w->p;
+    int Nrows = Cout;
+    if (up2) {      // bilinear x2 folded into the conv: 4 output phases, run on the low-resolution grid (pack.cu)
+        float* wexp;
+        MG_TRY(e->alloc(reinterpret_cast<void**>(&wexp), static_cast<size_t>(4) * Cout * Cin * 9 * 4));
+        MG_TRY(launch_up2_expand(w->p, wexp, Cout, Cin, st));
+        wsrc = wexp;
+        Nrows = 4 * Cout;
+    }
+    cw->N = Nrows; cw->cin = Cin; cw->caux = Caux; cw->taps = 9;
     cw->Ktot = 9 * Cin + Caux;
-    MG_TRY(e->alloc(&cw->w, static_cast<size_t>(Cout) * cw->Ktot * 2));
-    MG_TRY(launch_pack_conv(w->p, cw->w, e->bf16, Cout, Cin, 9, cw->Ktot, 0, st));
+    MG_TRY(e->alloc(&cw->w, static_cast<size_t>(Nrows) * cw->Ktot * 2));
+    MG_TRY(launch_pack_conv(wsrc, cw->w, e->bf16, Nrows, Cin, 9, cw->Ktot, 0, st));
     const float* b_in = nullptr;
     if (!in_key.empty()) {
         const RawWeight* wi;
@@ -252,9 +261,10 @@ static int pack_stack(moge_engine* e, const std::string& name, const moge_stack_
         if (!fold_head_out) {
             if (is_neck) {
                 if (sc.dim_in[l + 1] != 2) return set_error("neck: dim_in[%d] must be 2 (UV planes)", l + 1);
-                MG_TRY(pack_conv3(e, rs + ".1", C[l + 1], conv_cin, in_key, 0, true, &sw->post[l], st));
+                MG_TRY(pack_conv3(e, rs + ".1", C[l + 1], conv_cin, in_key, 0, true, &sw->post[l], st, sc.resamplers[l] == MOGE_RESAMPLE_BILINEAR));
             } else {
                 if (sc.dim_in[l + 1] <= 0) return set_error("%s: input block at level %d required", name.c_str(), l + 1);
+                if (sc.resamplers[l] == MOGE_RESAMPLE_BILINEAR) return set_error("%s: a bilinear resampler is supported at the last level only", name.c_str());
                 MG_TRY(pack_conv3(e, rs + ".1", C[l + 1], conv_cin, in_key, sc.dim_in[l + 1], false, &sw->post[l], st));
             }
         } else {
@@ -275,11 +285,16 @@ static int pack_stack(moge_engine* e, const std::string& name, const moge_stack_
             const int K9 = conv_cin * 9;
             MG_TRY(e->alloc(reinterpret_cast<void**>(&tmpw), static_cast<size_t>(16) * K9 * 4));
             CUDA_TRY(cudaMemsetAsync(tmpw, 0, static_cast<size_t>(16) * K9 * 4, st));
-            MG_TRY(launch_sgemm(wo->p, Cl, wc->p, K9, tmpw, K9, nc, K9, Cl, 0, st));          // [nc, (ci,tap)]
+            if (sc.resamplers[l] != MOGE_RESAMPLE_BILINEAR) return set_error("%s: the last resampler must be bilinear", name.c_str());
+            MG_TRY(launch_sgemm(wo->p, Cl, wc->p, K9, tmpw, K9, nc, K9, Cl, 0, st));          // [nc, (ci,tap)] = (nc,Cin,3,3)
+            float* wexp;                                                                       // (4*nc,Cin,3,3), rows (phase, comp)
+            MG_TRY(e->alloc(reinterpret_cast<void**>(&wexp), static_cast<size_t>(16) * K9 * 4));
+            CUDA_TRY(cudaMemsetAsync(wexp, 0, static_cast<size_t>(16) * K9 * 4, st));
+            MG_TRY(launch_up2_expand(tmpw, wexp, nc, conv_cin, st));
             ConvW& ho = sw->headout;
             ho.N = 16; ho.cin = conv_cin; ho.taps = 9; ho.Ktot = K9;
             MG_TRY(e->alloc(&ho.w, static_cast<size_t>(16) * K9 * 2));
-            MG_TRY(launch_pack_conv(tmpw, ho.w, e->bf16, 16, conv_cin, 9, K9, 0, st));
+            MG_TRY(launch_pack_conv(wexp, ho.w, e->bf16, 16, conv_cin, 9, K9, 0, st));
             MG_TRY(e->alloc(reinterpret_cast<void**>(&sw->waux), 3 * 32 * 4));
             CUDA_TRY(cudaMemsetAsync(sw->waux, 0, 3 * 32 * 4, st));
             MG_TRY(launch_sgemm(wo->p, Cl, w4->p, 32, sw->waux, 32, nc, 32, Cl, 0, st));       // [nc, 32]
@@ -430,7 +445,7 @@ static int add_conv(moge_engine* e, Plan* pl, const ConvW& cw, const void* src, 
     const double px = static_cast<double>(B) * gs.H * gs.W;
     const double flops = 2.0 * px * cw.N * cw.Ktot;
     double bytes = px * cw.cin * 2 + px * cw.caux * 2 + static_cast<double>(cw.N) * cw.Ktot * 2;
-    if (epi == EPI_HEADOUT) bytes += px * 32 * 2 + px * (ncomp == 1 ? 4 : 16);
+    if (epi == EPI_HEADOUT) bytes += 4 * px * 32 * 2 + 4 * px * (ncomp == 1 ? 4 : 16);     // 4 output pixels per low-res pixel
     else bytes += px * cw.N * 2 * ((out_raw ? 1 : 0) + (out_relu ? 1 : 0)) + (skip ? px * cw.N * 2 : 0);
     pl->ops.add([=](cudaStream_t st) { return launch_umma(bn, AMODE_TILES, epi, bf16, ma, mx, mb, p, sms, st); }, name, flops, bytes);
     return 0;
@@ -493,18 +508,20 @@ static int plan_stack(moge_engine* e, Plan* pl, const char* sname, const moge_st
             MG_TRY(add_conv(e, pl, sw.convT[l], x_raw, nullptr, g, B, EPI_DEC, sb.t_up[l + 1], nullptr, nullptr, gn, C[l + 1], true, false, 0, 0, nm("convT", l)));
             conv_src = sb.t_up[l + 1];
         } else {
-            void* up = sb.t_up[l + 1];
-            const bool bf16 = e->bf16;
-            const int Cl = C[l];
-            void* src = x_raw;
-            pl->ops.add([=](cudaStream_t st) { return launch_upsample2x(src, up, B, g.H, g.W, g.Hp, g.Wp, gn.Hp, gn.Wp, Cl, bf16, st); },
-                        nm("upsample2x", l), 0, static_cast<double>(B) * g.H * g.W * Cl * 2 * 5);
-            conv_src = up;
+            // bilinear x2 + 3x3 conv run as ONE low-resolution conv with 4 output phases (weights expanded at load time)
+            const bool need_relu_b = sc.num_res_blocks[l + 1] > 0;
+            if (tail) {
+                MG_TRY(add_conv(e, pl, sw.headout, x_raw, nullptr, g, B, EPI_HEADOUT, lowres_out, nullptr, neck_out[l + 1], gn, 0, false, false, 0, 0,
+                                nm("conv3x3up2.headout", l + 1), sw.ncomp, sw.waux));
+                break;
+            }
+            MG_TRY(add_conv(e, pl, sw.post[l], x_raw, nullptr, g, B, EPI_DEC, sb.x_raw[l + 1], need_relu_b ? sb.x_relu[l + 1] : nullptr, nullptr, gn,
+                            C[l + 1], true, is_neck, su, sv, nm("conv3x3up2.post", l + 1)));
+            x_raw = sb.x_raw[l + 1];
+            x_relu = sb.x_relu[l + 1];
+            continue;
         }
-        if (tail) {
-            MG_TRY(add_conv(e, pl, sw.headout, conv_src, nullptr, gn, B, EPI_HEADOUT, lowres_out, nullptr, neck_out[l + 1], gn, 0, false, false, 0, 0, nm("conv3x3.headout", l + 1), sw.ncomp, sw.waux));
-            break;
-        }
+        if (tail) return set_error("%s: the last resampler must be bilinear", sname);
         const bool need_relu = sc.num_res_blocks[l + 1] > 0;
         MG_TRY(add_conv(e, pl, sw.post[l], conv_src, is_neck ? nullptr : neck_out[l + 1], gn, B, EPI_DEC, sb.x_raw[l + 1],
                         need_relu ? sb.x_relu[l + 1] : nullptr, nullptr, gn, C[l + 1], false, is_neck, su, sv, nm("conv3x3.post", l + 1)));

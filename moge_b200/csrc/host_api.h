@@ -75,6 +75,8 @@ int launch_cast_2d(const void* src, int src_dtype, void* dst, bool bf16, int row
 int launch_pack_conv(const float* w, void* dst, bool bf16, int Cout, int Cin, int taps, int dst_ld, int k_off, cudaStream_t st);
 // dst16[(q*Cout + co), ci] = W[ci, co, q]  for ConvTranspose2d weight (Cin, Cout, 2, 2)
 int launch_pack_convT(const float* w, void* dst, bool bf16, int Cin, int Cout, cudaStream_t st);
+// (Cout,Cin,3,3) -> (4*Cout,Cin,3,3): bilinear-x2-upsample folded into the following 3x3 conv (see pack.cu)
+int launch_up2_expand(const float* w, float* dst, int Cout, int Cin, cudaStream_t st);
 // C[M,N] (fp32, ldc) = A[M,K] (lda) * B[K,N] (ldb)  (+ C if accumulate)   -- load-time only, SIMT
 int launch_sgemm(const float* A, int lda, const float* B, int ldb, float* C, int ldc, int M, int N, int K, int accumulate,
                  cudaStream_t st);

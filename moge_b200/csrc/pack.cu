@@ -74,6 +74,34 @@ int launch_pack_convT(const float* w, void* dst, bool bf16, int Cin, int Cout, c
     return 0;
 }
 
+// Bilinear x2 upsample (align_corners=False) followed by a 3x3 replicate-padded conv == four phase-specific 3x3
+// convs on the LOW-resolution map (exact, incl. the borders, when that map carries a replicated 1-pixel border):
+//   out[2i+py, 2j+px] = sum_{a,b} Weff[py,px][a,b] . in[i-1+a, j-1+b],   Weff = sum_{ky,kx} Uy[py][ky][a] Ux[px][kx][b] W[ky,kx]
+// src (Cout,Cin,3,3) fp32 -> dst (4*Cout,Cin,3,3) fp32 with row n = (py*2+px)*Cout + co.
+__global__ void up2_expand_kernel(const float* w, float* dst, int Cout, int Cin) {
+    // U[p][k][a]: weight of low-res tap a (offsets -1,0,+1) in upsampled row 2i+p-1+k
+    const float U[2][3][3] = {{{0.75f, 0.25f, 0.f}, {0.25f, 0.75f, 0.f}, {0.f, 0.75f, 0.25f}},
+                              {{0.25f, 0.75f, 0.f}, {0.f, 0.75f, 0.25f}, {0.f, 0.25f, 0.75f}}};
+    const size_t total = static_cast<size_t>(4) * Cout * Cin * 9;
+    for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total; i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        const int b = static_cast<int>(i % 3), a = static_cast<int>((i / 3) % 3);
+        const int ci = static_cast<int>((i / 9) % Cin);
+        const int n = static_cast<int>(i / (static_cast<size_t>(9) * Cin));
+        const int ph = n / Cout, co = n % Cout, py = ph >> 1, px = ph & 1;
+        const float* ws = w + (static_cast<size_t>(co) * Cin + ci) * 9;
+        float acc = 0.f;
+        for (int ky = 0; ky < 3; ++ky)
+            for (int kx = 0; kx < 3; ++kx) acc += U[py][ky][a] * U[px][kx][b] * ws[ky * 3 + kx];
+        dst[i] = acc;
+    }
+}
+int launch_up2_expand(const float* w, float* dst, int Cout, int Cin, cudaStream_t st) {
+    const size_t total = static_cast<size_t>(4) * Cout * Cin * 9;
+    up2_expand_kernel<<<static_cast<int>(std::min<size_t>((total + 255) / 256, 148 * 16)), 256, 0, st>>>(w, dst, Cout, Cin);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
 // C[M,N] = A[M,K] * B[K,N] (+C): 16x16 tiled fp32 SIMT, load time only.
 __global__ void sgemm_kernel(const float* A, int lda, const float* B, int ldb, float* C, int ldc, int M, int N, int K, int acc) {
     __shared__ float sa[16][17], sb[16][17];

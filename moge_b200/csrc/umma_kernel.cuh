@@ -22,7 +22,8 @@ enum : int {
     EPI_RESID = 2,     // x32[row, col] += gamma[col] * (acc + bias[col])            (fp32 residual stream, in place)
     EPI_PATCH = 3,     // x32[b*(T+1)+1+t, col] = acc + table[t, col]                (patch embed + pos embed)
     EPI_DEC = 4,       // padded-NHWC decoder store: acc + bias (+ UV rank-2) (+ skip) -> raw and/or ReLU copies
-    EPI_HEADOUT = 5,   // BN=16: folded head output projection + folded 1x1 of the neck level-4 map -> fp32 maps
+    EPI_HEADOUT = 5,   // BN=16: (bilinear x2 + 3x3 conv + output 1x1) folded into one low-res 3x3 conv with 4 output phases,
+                       //        + folded 1x1 of the high-res neck map -> fp32 maps at the high resolution
 };
 
 constexpr int TILE_M = 128;
@@ -225,26 +226,34 @@ umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
                 tmem_ld16(t_addr, v);
                 tc_wait_ld();
                 if (valid) {
-                    float o[3] = {v[0] + p.bias[0], v[1] + p.bias[1], v[2] + p.bias[2]};
-                    if (p.vec1 != nullptr) {
-                        const uint4* src = reinterpret_cast<const uint4*>(
-                            static_cast<const uint8_t*>(p.skip) + ((static_cast<size_t>(b) * p.Hop + py + 1) * p.Wop + px + 1) * 64);
+                    // accumulator columns: (phase, component); phase (qy,qx) -> output pixel (2*py+qy, 2*px+qx)
 #pragma unroll
-                        for (int q = 0; q < 4; ++q) {
-                            const uint4 u = src[q];
-                            const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+                    for (int ph = 0; ph < 4; ++ph) {
+                        const int Y = 2 * py + (ph >> 1), X = 2 * px + (ph & 1);
+                        float o[3];
 #pragma unroll
-                            for (int e = 0; e < 4; ++e) {
-                                const float2 f = H::unpack(w[e]);
-                                const int c = q * 8 + e * 2;
-                                for (int k = 0; k < 3; ++k)
-                                    if (k < p.ncomp) o[k] += p.vec1[k * 32 + c] * f.x + p.vec1[k * 32 + c + 1] * f.y;
+                        for (int k = 0; k < 3; ++k) o[k] = (k < p.ncomp) ? v[ph * p.ncomp + k] + p.bias[k] : 0.f;
+                        if (p.vec1 != nullptr) {
+                            const uint4* src = reinterpret_cast<const uint4*>(
+                                static_cast<const uint8_t*>(p.skip) + ((static_cast<size_t>(b) * p.Hop + Y + 1) * p.Wop + X + 1) * 64);
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) {
+                                const uint4 u = src[q];
+                                const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+                                for (int e = 0; e < 4; ++e) {
+                                    const float2 f = H::unpack(w[e]);
+                                    const int c = q * 8 + e * 2;
+#pragma unroll
+                                    for (int k = 0; k < 3; ++k)
+                                        if (k < p.ncomp) o[k] += p.vec1[k * 32 + c] * f.x + p.vec1[k * 32 + c + 1] * f.y;
+                                }
                             }
                         }
+                        const size_t pix = (static_cast<size_t>(b) * p.Ho + Y) * p.Wo + X;
+                        if (p.ncomp == 1) static_cast<float*>(p.out0)[pix] = o[0];
+                        else static_cast<float4*>(p.out0)[pix] = make_float4(o[0], o[1], o[2], 0.f);
                     }
-                    const size_t pix = (static_cast<size_t>(b) * p.Ho + py) * p.Wo + px;
-                    if (p.ncomp == 1) static_cast<float*>(p.out0)[pix] = o[0];
-                    else static_cast<float4*>(p.out0)[pix] = make_float4(o[0], o[1], o[2], 0.f);
                 }
                 __syncwarp();
             } else {
