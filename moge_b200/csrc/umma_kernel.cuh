@@ -260,11 +260,12 @@ umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
                 // ---- coordinates of the 8 rows this lane serves after the transpose (row = 4*i + sub of the warp's 32)
                 bool ok[8];
                 int rb[8], ry[8], rx[8];
-                size_t roff[8];
+                size_t roff[8];      // element offset of the row (ROWS epilogues) / BYTE offset of the centre output pixel (EPI_DEC)
+                int eflags[8];       // EPI_DEC: bit0 y==0, bit1 y==H-1, bit2 x==0, bit3 x==W-1 (source grid)
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
                     const int rl = quarter * 32 + 4 * i + sub;
-                    rb[i] = 0; ry[i] = 0; rx[i] = 0; roff[i] = 0;
+                    rb[i] = 0; ry[i] = 0; rx[i] = 0; roff[i] = 0; eflags[i] = 0;
                     if (AMODE == AMODE_ROWS) {
                         const long grow = static_cast<long>(mt) * TILE_M + rl;
                         ok[i] = grow < p.M;
@@ -283,7 +284,13 @@ umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
                         rx[i] = (r % p.tiles_x) * TILE_PW + rl % TILE_PW;
                         ok[i] = (ry[i] < p.H) && (rx[i] < p.W);
                     }
+                    if (EPI == EPI_DEC) {
+                        const int sh = p.shuffle ? 2 : 1;
+                        roff[i] = ((static_cast<size_t>(rb[i]) * p.Hop + sh * ry[i] + 1) * p.Wop + sh * rx[i] + 1) * p.ldo * 2;
+                        eflags[i] = (ry[i] == 0 ? 1 : 0) | (ry[i] == p.H - 1 ? 2 : 0) | (rx[i] == 0 ? 4 : 0) | (rx[i] == p.W - 1 ? 8 : 0);
+                    }
                 }
+                const float inv_wo = 1.0f / static_cast<float>(p.Wo), inv_ho = 1.0f / static_cast<float>(p.Ho);
 #pragma unroll 1
                 for (int c = 0; c < Cfg::kColsPerWarp; c += 32) {
                     float v[32];
@@ -296,10 +303,15 @@ umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
                     const int col = nt * BN + col_begin + c;       // first global output column of this chunk
                     int co = col + 4 * q4;                         // this lane's 4 columns
                     int qd = 0;
+                    size_t qoff = 0;                               // EPI_DEC: byte offset of this chunk relative to the centre pixel
+                    int qmask = 15;                                // which source-grid edges replicate for this chunk
                     if (EPI == EPI_DEC && p.shuffle) {
                         qd = col / p.ldo;                          // ldo == C_out; a 32-column chunk never straddles qd
                         co -= qd * p.ldo;
+                        qoff = (static_cast<size_t>(qd >> 1) * p.Wop + (qd & 1)) * p.ldo * 2;
+                        qmask = ((qd >> 1) ? 2 : 1) | ((qd & 1) ? 8 : 4);
                     }
+                    if (EPI == EPI_DEC) qoff += static_cast<size_t>(co) * 2;
                     float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f), g4 = bias4, h4 = bias4;
                     if (EPI != EPI_PATCH) bias4 = *reinterpret_cast<const float4*>(p.bias + co);
                     if (EPI == EPI_RESID) g4 = *reinterpret_cast<const float4*>(p.vec1 + co);
@@ -323,9 +335,7 @@ umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
                             const int t = ry[i] * p.W + rx[i];
                             pre[i] = *reinterpret_cast<const float4*>(p.vec1 + static_cast<size_t>(t) * p.ldo + co);
                         } else if (EPI == EPI_DEC && p.skip != nullptr) {
-                            const uint2 u = *reinterpret_cast<const uint2*>(
-                                static_cast<const uint8_t*>(p.skip) +
-                                (((static_cast<size_t>(rb[i]) * p.Hop + sY[i] + 1) * p.Wop + sX[i] + 1) * p.ldo + co) * 2);
+                            const uint2 u = *reinterpret_cast<const uint2*>(static_cast<const uint8_t*>(p.skip) + roff[i] + qoff);
                             const float2 f0 = H::unpack(u.x), f1 = H::unpack(u.y);
                             pre[i] = make_float4(f0.x, f0.y, f1.x, f1.y);
                         }
@@ -351,23 +361,25 @@ umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
                             *reinterpret_cast<float4*>(static_cast<float*>(p.out0) + roff[i] + co) =
                                 make_float4(a.x + pre[i].x, a.y + pre[i].y, a.z + pre[i].z, a.w + pre[i].w);
                         } else if (EPI == EPI_DEC) {
-                            const int Y = sY[i], X = sX[i];
                             a.x += bias4.x + pre[i].x; a.y += bias4.y + pre[i].y; a.z += bias4.z + pre[i].z; a.w += bias4.w + pre[i].w;
                             if (p.vec1 != nullptr) {
-                                const float uu = p.su * ((2 * X + 1) / static_cast<float>(p.Wo) - 1.0f);
-                                const float vv = p.sv * ((2 * Y + 1) / static_cast<float>(p.Ho) - 1.0f);
+                                const float uu = p.su * ((2 * sX[i] + 1) * inv_wo - 1.0f);
+                                const float vv = p.sv * ((2 * sY[i] + 1) * inv_ho - 1.0f);
                                 a.x += g4.x * uu + h4.x * vv; a.y += g4.y * uu + h4.y * vv;
                                 a.z += g4.z * uu + h4.z * vv; a.w += g4.w * uu + h4.w * vv;
                             }
+                            const bool edge = (eflags[i] & qmask) != 0;
                             if (p.out0 != nullptr) {
                                 uint2 pk;
                                 pk.x = H::pack(a.x, a.y); pk.y = H::pack(a.z, a.w);
-                                store_px_border8(static_cast<uint8_t*>(p.out0), rb[i], Y, X, p.Ho, p.Wo, p.Hop, p.Wop, p.ldo, co, pk);
+                                if (!edge) *reinterpret_cast<uint2*>(static_cast<uint8_t*>(p.out0) + roff[i] + qoff) = pk;
+                                else store_px_border8(static_cast<uint8_t*>(p.out0), rb[i], sY[i], sX[i], p.Ho, p.Wo, p.Hop, p.Wop, p.ldo, co, pk);
                             }
                             if (p.out1 != nullptr) {
                                 uint2 pk;
                                 pk.x = H::pack(fmaxf(a.x, 0.f), fmaxf(a.y, 0.f)); pk.y = H::pack(fmaxf(a.z, 0.f), fmaxf(a.w, 0.f));
-                                store_px_border8(static_cast<uint8_t*>(p.out1), rb[i], Y, X, p.Ho, p.Wo, p.Hop, p.Wop, p.ldo, co, pk);
+                                if (!edge) *reinterpret_cast<uint2*>(static_cast<uint8_t*>(p.out1) + roff[i] + qoff) = pk;
+                                else store_px_border8(static_cast<uint8_t*>(p.out1), rb[i], sY[i], sX[i], p.Ho, p.Wo, p.Hop, p.Wop, p.ldo, co, pk);
                             }
                         }
                     }
