@@ -1,0 +1,149 @@
+// 3x3 replicate-padded convolution for 64-channel inputs (decoder levels 3 and 4 -- the HBM-bound end of the pyramid).
+// Same tcgen05/TMEM machinery and the same epilogues as umma_kernel<TILES>, but with the two changes that matter when
+// K per tap is a single 64-channel block:
+//   * the packed weights of this CTA's output-channel tile (9 taps [+ the fused 1x1 input block]) are loaded ONCE and
+//     stay resident in shared memory for the whole persistent loop;
+//   * the input halo is fetched as 3 boxes per tile (one per horizontal tap offset, 16 px x 10 rows) instead of 9: the
+//     three vertical taps of a box are 2 KB-aligned row windows of the same box, so each becomes a UMMA A operand
+//     without another copy (L2->SM traffic 3.75x the tile instead of 9x + weights).
+#pragma once
+#include "umma_kernel.cuh"
+
+namespace mg {
+
+template <int BN> struct Conv64Cfg {
+    static constexpr int kABytes = 160 * 128;                       // box {64 ch, 16 px, 10 rows}
+    static constexpr int kWBytes = BN * 128 * 10;                   // 9 taps + 1 aux block, each [BN][64] 128B-swizzled
+    static constexpr int kStages = (BN >= 64) ? 5 : 6;
+    static constexpr int kEpiWarps = (BN >= 64) ? 8 : 4;
+    static constexpr int kThreads = 64 + 32 * kEpiWarps;
+    static constexpr int kTmemCols = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : 128;
+    static constexpr int kScratchBytes = kEpiWarps * 4096;
+    static constexpr int kSmemBytes = kStages * kABytes + kWBytes + 1024 + 256 + kScratchBytes;
+    static constexpr int kColsPerWarp = (kEpiWarps == 8) ? BN / 2 : BN;
+};
+
+template <int BN, int EPI, bool BF16>
+__global__ void __launch_bounds__(Conv64Cfg<BN>::kThreads, 1)
+conv64_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapAux,
+              const __grid_constant__ CUtensorMap mapW, const UmmaParams p) {
+    using Cfg = Conv64Cfg<BN>;
+    constexpr int S = Cfg::kStages;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint8_t* sW = smem + S * Cfg::kABytes;
+    uint64_t* full = reinterpret_cast<uint64_t*>(sW + Cfg::kWBytes);
+    uint64_t* empty = full + S;
+    uint64_t* tfull = empty + S;
+    uint64_t* tempty = tfull + 2;
+    uint64_t* wfull = tempty + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wfull + 1);
+    float* scratch_base = reinterpret_cast<float*>(sW + Cfg::kWBytes + 256);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nnt = p.num_n_tiles;
+    const int nt = blockIdx.x % nnt;                  // this CTA's output-channel tile (weights stay resident)
+    const int mt0 = blockIdx.x / nnt, mstep = gridDim.x / nnt;
+    const int nstage = 3 + p.kb_aux;                  // stages per tile: dx = 0,1,2 (+ the 1x1 aux source)
+
+    if (threadIdx.x == 0) {
+        tma_prefetch_desc(&mapA);
+        tma_prefetch_desc(&mapW);
+        if (p.kb_aux) tma_prefetch_desc(&mapAux);
+        for (int s = 0; s < S; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], Cfg::kEpiWarps); }
+        mbar_init(wfull, 1);
+        fence_mbar_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, Cfg::kTmemCols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            const int nblk = 9 + p.kb_aux;
+            mbar_arrive_expect_tx(wfull, nblk * BN * 128);
+            for (int t = 0; t < nblk; ++t) tma_load_2d(sW + t * BN * 128, &mapW, wfull, t * TILE_K, nt * BN);
+            int s = 0; uint32_t ph = 0;
+            const int per_img = p.tiles_x * p.tiles_y;
+            for (int mt = mt0; mt < p.num_m_tiles; mt += mstep) {
+                const int b = mt / per_img, r = mt % per_img;
+                const int y0 = (r / p.tiles_x) * TILE_PH, x0 = (r % p.tiles_x) * TILE_PW;
+                for (int i = 0; i < nstage; ++i) {
+                    mbar_wait(&empty[s], ph ^ 1);
+                    uint8_t* sa = smem + s * Cfg::kABytes;
+                    if (i < 3) {
+                        mbar_arrive_expect_tx(&full[s], Cfg::kABytes);
+                        tma_load_4d(sa, &mapA, &full[s], 0, x0 + i, y0, b);          // padded rows y0..y0+9 = taps dy 0..2
+                    } else {
+                        mbar_arrive_expect_tx(&full[s], TILE_M * 128);
+                        tma_load_4d(sa, &mapAux, &full[s], 0, x0 + 1, y0 + 1, b);
+                    }
+                    if (++s == S) { s = 0; ph ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc(TILE_M, BN, BF16 ? 1u : 0u);
+            mbar_wait(wfull, 0);
+            int s = 0; uint32_t ph = 0;
+            int it = 0;
+            const uint32_t w0 = smem_u32(sW);
+            for (int mt = mt0; mt < p.num_m_tiles; mt += mstep, ++it) {
+                const int acc = it & 1;
+                mbar_wait(&tempty[acc], ((it >> 1) & 1) ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * BN;
+                for (int i = 0; i < nstage; ++i) {
+                    mbar_wait(&full[s], ph);
+                    tc_fence_after();
+                    const uint32_t sa = smem_u32(smem + s * Cfg::kABytes);
+                    if (i < 3) {
+#pragma unroll
+                        for (int dy = 0; dy < 3; ++dy) {
+                            const uint64_t adesc = make_sdesc_sw128(sa + dy * TILE_PW * 128);
+                            const uint64_t bdesc = make_sdesc_sw128(w0 + (dy * 3 + i) * BN * 128);
+#pragma unroll
+                            for (int k = 0; k < TILE_K / 16; ++k) umma_f16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (i | dy | k) != 0);
+                        }
+                    } else {
+                        const uint64_t adesc = make_sdesc_sw128(sa);
+                        const uint64_t bdesc = make_sdesc_sw128(w0 + 9 * BN * 128);
+#pragma unroll
+                        for (int k = 0; k < TILE_K / 16; ++k) umma_f16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, 1);
+                    }
+                    umma_commit(&empty[s]);
+                    if (++s == S) { s = 0; ph ^= 1; }
+                }
+                umma_commit(&tfull[acc]);
+            }
+        }
+    } else {
+        const int ew = warp - 2;
+        const int quarter = warp & 3;
+        const int col_begin = (Cfg::kEpiWarps == 8) ? (ew >> 2) * (BN / 2) : 0;
+        float4* scr = reinterpret_cast<float4*>(scratch_base + ew * 1024);
+        int it = 0;
+        for (int mt = mt0; mt < p.num_m_tiles; mt += mstep, ++it) {
+            const int acc = it & 1;
+            mbar_wait(&tfull[acc], (it >> 1) & 1);
+            tc_fence_after();
+            const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN + col_begin;
+            epilogue_tile<BN, Cfg::kColsPerWarp, AMODE_TILES, EPI, BF16>(p, mt, nt, t_addr, scr, quarter, lane, col_begin);
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty[acc]);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, Cfg::kTmemCols);
+    }
+}
+
+}  // namespace mg

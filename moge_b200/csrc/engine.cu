@@ -436,17 +436,30 @@ static int add_conv(moge_engine* e, Plan* pl, const ConvW& cw, const void* src, 
     p.Ho = go.H; p.Wo = go.W; p.Hop = go.Hp; p.Wop = go.Wp;
     p.shuffle = shuffle ? 1 : 0; p.su = su; p.sv = sv;
     if (epi == EPI_HEADOUT) { p.vec1 = waux; p.ncomp = ncomp; }
-    CUtensorMap ma, mx, mb;
-    MG_TRY(make_map_nhwc(&ma, src, cw.cin, gs.Wp, gs.Hp, B));
-    if (cw.caux) MG_TRY(make_map_nhwc(&mx, aux, cw.caux, gs.Wp, gs.Hp, B));
-    else mx = ma;
-    MG_TRY(make_map_2d(&mb, cw.w, cw.Ktot, cw.N, cw.Ktot, bn));
     const bool bf16 = e->bf16; const int sms = e->num_sms;
     const double px = static_cast<double>(B) * gs.H * gs.W;
     const double flops = 2.0 * px * cw.N * cw.Ktot;
     double bytes = px * cw.cin * 2 + px * cw.caux * 2 + static_cast<double>(cw.N) * cw.Ktot * 2;
     if (epi == EPI_HEADOUT) bytes += 4 * px * 32 * 2 + 4 * px * (ncomp == 1 ? 4 : 16);     // 4 output pixels per low-res pixel
     else bytes += px * cw.N * 2 * ((out_raw ? 1 : 0) + (out_relu ? 1 : 0)) + (skip ? px * cw.N * 2 : 0);
+    CUtensorMap ma, mx, mb;
+    // C_in = 64 3x3 convs (levels 3/4): resident weights + one halo box per horizontal tap (conv64_kernel.cuh)
+    const bool use64 = cw.taps == 9 && cw.cin == 64 && (cw.caux == 0 || cw.caux == 64) && gs.Hp >= 10 &&
+                       ((epi == EPI_HEADOUT && cw.N == 16) || (epi == EPI_DEC && cw.N % 64 == 0));
+    if (use64) {
+        const int bn64 = (epi == EPI_HEADOUT) ? 16 : 64;
+        p.num_n_tiles = cw.N / bn64;
+        MG_TRY(make_map_nhwc(&ma, src, cw.cin, gs.Wp, gs.Hp, B, 10));
+        if (cw.caux) MG_TRY(make_map_nhwc(&mx, aux, cw.caux, gs.Wp, gs.Hp, B, 8));
+        else mx = ma;
+        MG_TRY(make_map_2d(&mb, cw.w, cw.Ktot, cw.N, cw.Ktot, bn64));
+        pl->ops.add([=](cudaStream_t st) { return launch_conv64(bn64, epi, bf16, ma, mx, mb, p, sms, st); }, name, flops, bytes);
+        return 0;
+    }
+    MG_TRY(make_map_nhwc(&ma, src, cw.cin, gs.Wp, gs.Hp, B));
+    if (cw.caux) MG_TRY(make_map_nhwc(&mx, aux, cw.caux, gs.Wp, gs.Hp, B));
+    else mx = ma;
+    MG_TRY(make_map_2d(&mb, cw.w, cw.Ktot, cw.N, cw.Ktot, bn));
     pl->ops.add([=](cudaStream_t st) { return launch_umma(bn, AMODE_TILES, epi, bf16, ma, mx, mb, p, sms, st); }, name, flops, bytes);
     return 0;
 }
@@ -913,9 +926,16 @@ int moge_op_conv(const void* x, const float* w, const float* bias, const void* s
         p.out0 = out_raw; p.out1 = out_relu; p.bias = bias; p.skip = skip; p.ldo = Cout;
         p.Ho = go.H; p.Wo = go.W; p.Hop = go.Hp; p.Wop = go.Wp; p.shuffle = shuffle;
         CUtensorMap ma, mb;
-        rc = make_map_nhwc(&ma, x, Cin, gs.Wp, gs.Hp, B);
-        if (rc == 0) rc = make_map_2d(&mb, wp, Ktot, N, Ktot, bn);
-        if (rc == 0) rc = launch_umma(bn, AMODE_TILES, EPI_DEC, bf16, ma, ma, mb, p, dev_sms(), st);
+        if (taps == 9 && Cin == 64 && N % 64 == 0 && gs.Hp >= 10) {
+            p.num_n_tiles = N / 64;
+            rc = make_map_nhwc(&ma, x, Cin, gs.Wp, gs.Hp, B, 10);
+            if (rc == 0) rc = make_map_2d(&mb, wp, Ktot, N, Ktot, 64);
+            if (rc == 0) rc = launch_conv64(64, EPI_DEC, bf16, ma, ma, mb, p, dev_sms(), st);
+        } else {
+            rc = make_map_nhwc(&ma, x, Cin, gs.Wp, gs.Hp, B);
+            if (rc == 0) rc = make_map_2d(&mb, wp, Ktot, N, Ktot, bn);
+            if (rc == 0) rc = launch_umma(bn, AMODE_TILES, EPI_DEC, bf16, ma, ma, mb, p, dev_sms(), st);
+        }
     }
     cudaStreamSynchronize(st);
     cudaFree(wp);

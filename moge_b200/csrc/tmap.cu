@@ -64,10 +64,10 @@ int make_map_3d(CUtensorMap* m, const void* base, uint64_t cols, uint64_t rows, 
     cuuint32_t box[3] = {64, box_rows, 1};
     return encode(m, base, 3, dims, strides, box);
 }
-int make_map_nhwc(CUtensorMap* m, const void* base, uint64_t C, uint64_t Wp, uint64_t Hp, uint64_t B) {
+int make_map_nhwc(CUtensorMap* m, const void* base, uint64_t C, uint64_t Wp, uint64_t Hp, uint64_t B, uint32_t box_rows) {
     cuuint64_t dims[4] = {C, Wp, Hp, B};
     cuuint64_t strides[3] = {C * 2, C * Wp * 2, C * Wp * Hp * 2};
-    cuuint32_t box[4] = {64, 16, 8, 1};
+    cuuint32_t box[4] = {64, 16, box_rows, 1};
     if (C % 64) return set_error("NHWC tensor map needs C %% 64 == 0 (C=%llu)", (unsigned long long)C);
     return encode(m, base, 4, dims, strides, box);
 }

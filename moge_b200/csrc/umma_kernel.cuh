@@ -97,6 +97,191 @@ __device__ __forceinline__ void store_px_border8(uint8_t* base, int b, int Y, in
             if (dy != 0 || dx != 0) *reinterpret_cast<uint2*>(centre + dy * rowp + dx * colp) = q;
 }
 
+// Epilogue of ONE accumulator tile for one epilogue warp (TMEM lane quarter `quarter`, columns [col_begin, col_begin+COLS)).
+// TMEM hands each thread one accumulator ROW; global memory wants warps on contiguous COLUMNS.  Every 32x32 chunk is
+// therefore transposed through a per-warp swizzled smem tile: afterwards 8 lanes x float4 cover the 32 columns of one
+// row and each warp instruction touches 4 rows (4 x 128 B), fully coalesced.
+template <int BN, int COLS, int AMODE, int EPI, bool BF16>
+__device__ __forceinline__ void epilogue_tile(const UmmaParams& p, int mt, int nt, uint32_t t_addr, float4* scr, int quarter,
+                                              int lane, int col_begin) {
+    using H = H16<BF16>;
+    const int row = quarter * 32 + lane;
+    const int sub = lane >> 3;        // which of the 4 rows of a pass this lane serves
+    const int q4 = lane & 7;          // which float4 (4 columns) of the 32-column chunk
+    if (EPI == EPI_HEADOUT) {
+        // lane = pixel: 16 B (or 4 B) per lane, consecutive lanes = consecutive pixels of a tile row
+        const int per_img = p.tiles_x * p.tiles_y;
+        const int b = mt / per_img;
+        const int r = mt % per_img;
+        const int py = (r / p.tiles_x) * TILE_PH + row / TILE_PW;
+        const int px = (r % p.tiles_x) * TILE_PW + row % TILE_PW;
+        const bool valid = (py < p.H) && (px < p.W);
+        float v[16];
+        tmem_ld16(t_addr, v);
+        tc_wait_ld();
+        if (valid) {
+            // accumulator columns: (phase, component); phase (qy,qx) -> output pixel (2*py+qy, 2*px+qx)
+#pragma unroll
+            for (int ph = 0; ph < 4; ++ph) {
+                const int Y = 2 * py + (ph >> 1), X = 2 * px + (ph & 1);
+                float o[3];
+#pragma unroll
+                for (int k = 0; k < 3; ++k) o[k] = (k < p.ncomp) ? v[ph * p.ncomp + k] + p.bias[k] : 0.f;
+                if (p.vec1 != nullptr) {
+                    const uint4* src = reinterpret_cast<const uint4*>(
+                        static_cast<const uint8_t*>(p.skip) + ((static_cast<size_t>(b) * p.Hop + Y + 1) * p.Wop + X + 1) * 64);
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const uint4 u = src[q];
+                        const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const float2 f = H::unpack(w[e]);
+                            const int c = q * 8 + e * 2;
+#pragma unroll
+                            for (int k = 0; k < 3; ++k)
+                                if (k < p.ncomp) o[k] += p.vec1[k * 32 + c] * f.x + p.vec1[k * 32 + c + 1] * f.y;
+                        }
+                    }
+                }
+                const size_t pix = (static_cast<size_t>(b) * p.Ho + Y) * p.Wo + X;
+                if (p.ncomp == 1) static_cast<float*>(p.out0)[pix] = o[0];
+                else static_cast<float4*>(p.out0)[pix] = make_float4(o[0], o[1], o[2], 0.f);
+            }
+        }
+        __syncwarp();
+    } else {
+        // ---- coordinates of the 8 rows this lane serves after the transpose (row = 4*i + sub of the warp's 32)
+        bool ok[8];
+        int rb[8], ry[8], rx[8];
+        size_t roff[8];      // element offset of the row (ROWS epilogues) / BYTE offset of the centre output pixel (EPI_DEC)
+        int eflags[8];       // EPI_DEC: bit0 y==0, bit1 y==H-1, bit2 x==0, bit3 x==W-1 (source grid)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int rl = quarter * 32 + 4 * i + sub;
+            rb[i] = 0; ry[i] = 0; rx[i] = 0; roff[i] = 0; eflags[i] = 0;
+            if (AMODE == AMODE_ROWS) {
+                const long grow = static_cast<long>(mt) * TILE_M + rl;
+                ok[i] = grow < p.M;
+                roff[i] = static_cast<size_t>(grow) * p.ldo;
+                if (EPI == EPI_DEC || EPI == EPI_PATCH) {
+                    rb[i] = static_cast<int>(grow / p.T);
+                    const int t = static_cast<int>(grow % p.T);
+                    ry[i] = t / p.W; rx[i] = t % p.W;
+                    if (EPI == EPI_PATCH) roff[i] = (static_cast<size_t>(rb[i]) * (p.T + 1) + 1 + t) * p.ldo;
+                }
+            } else {
+                const int per_img = p.tiles_x * p.tiles_y;
+                rb[i] = mt / per_img;
+                const int r = mt % per_img;
+                ry[i] = (r / p.tiles_x) * TILE_PH + rl / TILE_PW;
+                rx[i] = (r % p.tiles_x) * TILE_PW + rl % TILE_PW;
+                ok[i] = (ry[i] < p.H) && (rx[i] < p.W);
+            }
+            if (EPI == EPI_DEC) {
+                const int sh = p.shuffle ? 2 : 1;
+                roff[i] = ((static_cast<size_t>(rb[i]) * p.Hop + sh * ry[i] + 1) * p.Wop + sh * rx[i] + 1) * p.ldo * 2;
+                eflags[i] = (ry[i] == 0 ? 1 : 0) | (ry[i] == p.H - 1 ? 2 : 0) | (rx[i] == 0 ? 4 : 0) | (rx[i] == p.W - 1 ? 8 : 0);
+            }
+        }
+        const float inv_wo = 1.0f / static_cast<float>(p.Wo), inv_ho = 1.0f / static_cast<float>(p.Ho);
+#pragma unroll 1
+        for (int c = 0; c < COLS; c += 32) {
+            float v[32];
+            tmem_ld32(t_addr + c, v);
+            tc_wait_ld();
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+                scr[lane * 8 + (q ^ (lane & 7))] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+            __syncwarp();
+            const int col = nt * BN + col_begin + c;       // first global output column of this chunk
+            int co = col + 4 * q4;                         // this lane's 4 columns
+            int qd = 0;
+            size_t qoff = 0;                               // EPI_DEC: byte offset of this chunk relative to the centre pixel
+            int qmask = 15;                                // which source-grid edges replicate for this chunk
+            if (EPI == EPI_DEC && p.shuffle) {
+                qd = col / p.ldo;                          // ldo == C_out; a 32-column chunk never straddles qd
+                co -= qd * p.ldo;
+                qoff = (static_cast<size_t>(qd >> 1) * p.Wop + (qd & 1)) * p.ldo * 2;
+                qmask = ((qd >> 1) ? 2 : 1) | ((qd & 1) ? 8 : 4);
+            }
+            if (EPI == EPI_DEC) qoff += static_cast<size_t>(co) * 2;
+            float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f), g4 = bias4, h4 = bias4;
+            if (EPI != EPI_PATCH) bias4 = *reinterpret_cast<const float4*>(p.bias + co);
+            if (EPI == EPI_RESID) g4 = *reinterpret_cast<const float4*>(p.vec1 + co);
+            if (EPI == EPI_DEC && p.vec1 != nullptr) {
+                g4 = *reinterpret_cast<const float4*>(p.vec1 + co);
+                h4 = *reinterpret_cast<const float4*>(p.vec2 + co);
+            }
+            // ---- phase 1: issue every global READ of this chunk (residual / pos table / skip) back to back, so
+            //      their L2 latencies overlap instead of serialising behind the stores of the previous row
+            float4 pre[8];
+            int sY[8], sX[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                pre[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                sY[i] = ry[i]; sX[i] = rx[i];
+                if (EPI == EPI_DEC && p.shuffle) { sY[i] = 2 * ry[i] + (qd >> 1); sX[i] = 2 * rx[i] + (qd & 1); }
+                if (!ok[i]) continue;
+                if (EPI == EPI_RESID) {
+                    pre[i] = *reinterpret_cast<const float4*>(static_cast<const float*>(p.out0) + roff[i] + co);
+                } else if (EPI == EPI_PATCH) {
+                    const int t = ry[i] * p.W + rx[i];
+                    pre[i] = *reinterpret_cast<const float4*>(p.vec1 + static_cast<size_t>(t) * p.ldo + co);
+                } else if (EPI == EPI_DEC && p.skip != nullptr) {
+                    const uint2 u = *reinterpret_cast<const uint2*>(static_cast<const uint8_t*>(p.skip) + roff[i] + qoff);
+                    const float2 f0 = H::unpack(u.x), f1 = H::unpack(u.y);
+                    pre[i] = make_float4(f0.x, f0.y, f1.x, f1.y);
+                }
+            }
+            // ---- phase 2: math + stores
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int rl = 4 * i + sub;
+                float4 a = scr[rl * 8 + (q4 ^ (rl & 7))];
+                if (!ok[i]) continue;
+                if (EPI == EPI_STORE16 || EPI == EPI_GELU16) {
+                    a.x += bias4.x; a.y += bias4.y; a.z += bias4.z; a.w += bias4.w;
+                    if (EPI == EPI_GELU16) { a.x = gelu_erf(a.x); a.y = gelu_erf(a.y); a.z = gelu_erf(a.z); a.w = gelu_erf(a.w); }
+                    uint2 pk;
+                    pk.x = H::pack(a.x, a.y); pk.y = H::pack(a.z, a.w);
+                    *reinterpret_cast<uint2*>(static_cast<typename H::T*>(p.out0) + roff[i] + co) = pk;
+                } else if (EPI == EPI_RESID) {
+                    float4 x = pre[i];
+                    x.x += g4.x * (a.x + bias4.x); x.y += g4.y * (a.y + bias4.y);
+                    x.z += g4.z * (a.z + bias4.z); x.w += g4.w * (a.w + bias4.w);
+                    *reinterpret_cast<float4*>(static_cast<float*>(p.out0) + roff[i] + co) = x;
+                } else if (EPI == EPI_PATCH) {
+                    *reinterpret_cast<float4*>(static_cast<float*>(p.out0) + roff[i] + co) =
+                        make_float4(a.x + pre[i].x, a.y + pre[i].y, a.z + pre[i].z, a.w + pre[i].w);
+                } else if (EPI == EPI_DEC) {
+                    a.x += bias4.x + pre[i].x; a.y += bias4.y + pre[i].y; a.z += bias4.z + pre[i].z; a.w += bias4.w + pre[i].w;
+                    if (p.vec1 != nullptr) {
+                        const float uu = p.su * ((2 * sX[i] + 1) * inv_wo - 1.0f);
+                        const float vv = p.sv * ((2 * sY[i] + 1) * inv_ho - 1.0f);
+                        a.x += g4.x * uu + h4.x * vv; a.y += g4.y * uu + h4.y * vv;
+                        a.z += g4.z * uu + h4.z * vv; a.w += g4.w * uu + h4.w * vv;
+                    }
+                    const bool edge = (eflags[i] & qmask) != 0;
+                    if (p.out0 != nullptr) {
+                        uint2 pk;
+                        pk.x = H::pack(a.x, a.y); pk.y = H::pack(a.z, a.w);
+                        if (!edge) *reinterpret_cast<uint2*>(static_cast<uint8_t*>(p.out0) + roff[i] + qoff) = pk;
+                        else store_px_border8(static_cast<uint8_t*>(p.out0), rb[i], sY[i], sX[i], p.Ho, p.Wo, p.Hop, p.Wop, p.ldo, co, pk);
+                    }
+                    if (p.out1 != nullptr) {
+                        uint2 pk;
+                        pk.x = H::pack(fmaxf(a.x, 0.f), fmaxf(a.y, 0.f)); pk.y = H::pack(fmaxf(a.z, 0.f), fmaxf(a.w, 0.f));
+                        if (!edge) *reinterpret_cast<uint2*>(static_cast<uint8_t*>(p.out1) + roff[i] + qoff) = pk;
+                        else store_px_border8(static_cast<uint8_t*>(p.out1), rb[i], sY[i], sX[i], p.Ho, p.Wo, p.Hop, p.Wop, p.ldo, co, pk);
+                    }
+                }
+            }
+            __syncwarp();
+        }
+    }
+}
+
 template <int BN, int AMODE, int EPI, bool BF16>
 __global__ void __launch_bounds__(UmmaCfg<BN>::kThreads, 1)
 umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapAux,
@@ -201,10 +386,7 @@ umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
         const int ew = warp - 2;
         const int quarter = warp & 3;
         const int col_begin = (Cfg::kEpiWarps == 8) ? (ew >> 2) * (BN / 2) : 0;
-        const int row = quarter * 32 + lane;
         float4* scr = reinterpret_cast<float4*>(scratch_base + ew * 1024);
-        const int sub = lane >> 3;        // which of the 4 rows of a pass this lane serves
-        const int q4 = lane & 7;          // which float4 (4 columns) of the 32-column chunk
         int it = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
             const int mt = tile / p.num_n_tiles, nt = tile % p.num_n_tiles;
@@ -214,178 +396,7 @@ umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
             tc_fence_after();
             const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN + col_begin;
 
-            if (EPI == EPI_HEADOUT) {
-                // lane = pixel: 16 B (or 4 B) per lane, consecutive lanes = consecutive pixels of a tile row
-                const int per_img = p.tiles_x * p.tiles_y;
-                const int b = mt / per_img;
-                const int r = mt % per_img;
-                const int py = (r / p.tiles_x) * TILE_PH + row / TILE_PW;
-                const int px = (r % p.tiles_x) * TILE_PW + row % TILE_PW;
-                const bool valid = (py < p.H) && (px < p.W);
-                float v[16];
-                tmem_ld16(t_addr, v);
-                tc_wait_ld();
-                if (valid) {
-                    // accumulator columns: (phase, component); phase (qy,qx) -> output pixel (2*py+qy, 2*px+qx)
-#pragma unroll
-                    for (int ph = 0; ph < 4; ++ph) {
-                        const int Y = 2 * py + (ph >> 1), X = 2 * px + (ph & 1);
-                        float o[3];
-#pragma unroll
-                        for (int k = 0; k < 3; ++k) o[k] = (k < p.ncomp) ? v[ph * p.ncomp + k] + p.bias[k] : 0.f;
-                        if (p.vec1 != nullptr) {
-                            const uint4* src = reinterpret_cast<const uint4*>(
-                                static_cast<const uint8_t*>(p.skip) + ((static_cast<size_t>(b) * p.Hop + Y + 1) * p.Wop + X + 1) * 64);
-#pragma unroll
-                            for (int q = 0; q < 4; ++q) {
-                                const uint4 u = src[q];
-                                const uint32_t w[4] = {u.x, u.y, u.z, u.w};
-#pragma unroll
-                                for (int e = 0; e < 4; ++e) {
-                                    const float2 f = H::unpack(w[e]);
-                                    const int c = q * 8 + e * 2;
-#pragma unroll
-                                    for (int k = 0; k < 3; ++k)
-                                        if (k < p.ncomp) o[k] += p.vec1[k * 32 + c] * f.x + p.vec1[k * 32 + c + 1] * f.y;
-                                }
-                            }
-                        }
-                        const size_t pix = (static_cast<size_t>(b) * p.Ho + Y) * p.Wo + X;
-                        if (p.ncomp == 1) static_cast<float*>(p.out0)[pix] = o[0];
-                        else static_cast<float4*>(p.out0)[pix] = make_float4(o[0], o[1], o[2], 0.f);
-                    }
-                }
-                __syncwarp();
-            } else {
-                // ---- coordinates of the 8 rows this lane serves after the transpose (row = 4*i + sub of the warp's 32)
-                bool ok[8];
-                int rb[8], ry[8], rx[8];
-                size_t roff[8];      // element offset of the row (ROWS epilogues) / BYTE offset of the centre output pixel (EPI_DEC)
-                int eflags[8];       // EPI_DEC: bit0 y==0, bit1 y==H-1, bit2 x==0, bit3 x==W-1 (source grid)
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const int rl = quarter * 32 + 4 * i + sub;
-                    rb[i] = 0; ry[i] = 0; rx[i] = 0; roff[i] = 0; eflags[i] = 0;
-                    if (AMODE == AMODE_ROWS) {
-                        const long grow = static_cast<long>(mt) * TILE_M + rl;
-                        ok[i] = grow < p.M;
-                        roff[i] = static_cast<size_t>(grow) * p.ldo;
-                        if (EPI == EPI_DEC || EPI == EPI_PATCH) {
-                            rb[i] = static_cast<int>(grow / p.T);
-                            const int t = static_cast<int>(grow % p.T);
-                            ry[i] = t / p.W; rx[i] = t % p.W;
-                            if (EPI == EPI_PATCH) roff[i] = (static_cast<size_t>(rb[i]) * (p.T + 1) + 1 + t) * p.ldo;
-                        }
-                    } else {
-                        const int per_img = p.tiles_x * p.tiles_y;
-                        rb[i] = mt / per_img;
-                        const int r = mt % per_img;
-                        ry[i] = (r / p.tiles_x) * TILE_PH + rl / TILE_PW;
-                        rx[i] = (r % p.tiles_x) * TILE_PW + rl % TILE_PW;
-                        ok[i] = (ry[i] < p.H) && (rx[i] < p.W);
-                    }
-                    if (EPI == EPI_DEC) {
-                        const int sh = p.shuffle ? 2 : 1;
-                        roff[i] = ((static_cast<size_t>(rb[i]) * p.Hop + sh * ry[i] + 1) * p.Wop + sh * rx[i] + 1) * p.ldo * 2;
-                        eflags[i] = (ry[i] == 0 ? 1 : 0) | (ry[i] == p.H - 1 ? 2 : 0) | (rx[i] == 0 ? 4 : 0) | (rx[i] == p.W - 1 ? 8 : 0);
-                    }
-                }
-                const float inv_wo = 1.0f / static_cast<float>(p.Wo), inv_ho = 1.0f / static_cast<float>(p.Ho);
-#pragma unroll 1
-                for (int c = 0; c < Cfg::kColsPerWarp; c += 32) {
-                    float v[32];
-                    tmem_ld32(t_addr + c, v);
-                    tc_wait_ld();
-#pragma unroll
-                    for (int q = 0; q < 8; ++q)
-                        scr[lane * 8 + (q ^ (lane & 7))] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
-                    __syncwarp();
-                    const int col = nt * BN + col_begin + c;       // first global output column of this chunk
-                    int co = col + 4 * q4;                         // this lane's 4 columns
-                    int qd = 0;
-                    size_t qoff = 0;                               // EPI_DEC: byte offset of this chunk relative to the centre pixel
-                    int qmask = 15;                                // which source-grid edges replicate for this chunk
-                    if (EPI == EPI_DEC && p.shuffle) {
-                        qd = col / p.ldo;                          // ldo == C_out; a 32-column chunk never straddles qd
-                        co -= qd * p.ldo;
-                        qoff = (static_cast<size_t>(qd >> 1) * p.Wop + (qd & 1)) * p.ldo * 2;
-                        qmask = ((qd >> 1) ? 2 : 1) | ((qd & 1) ? 8 : 4);
-                    }
-                    if (EPI == EPI_DEC) qoff += static_cast<size_t>(co) * 2;
-                    float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f), g4 = bias4, h4 = bias4;
-                    if (EPI != EPI_PATCH) bias4 = *reinterpret_cast<const float4*>(p.bias + co);
-                    if (EPI == EPI_RESID) g4 = *reinterpret_cast<const float4*>(p.vec1 + co);
-                    if (EPI == EPI_DEC && p.vec1 != nullptr) {
-                        g4 = *reinterpret_cast<const float4*>(p.vec1 + co);
-                        h4 = *reinterpret_cast<const float4*>(p.vec2 + co);
-                    }
-                    // ---- phase 1: issue every global READ of this chunk (residual / pos table / skip) back to back, so
-                    //      their L2 latencies overlap instead of serialising behind the stores of the previous row
-                    float4 pre[8];
-                    int sY[8], sX[8];
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        pre[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-                        sY[i] = ry[i]; sX[i] = rx[i];
-                        if (EPI == EPI_DEC && p.shuffle) { sY[i] = 2 * ry[i] + (qd >> 1); sX[i] = 2 * rx[i] + (qd & 1); }
-                        if (!ok[i]) continue;
-                        if (EPI == EPI_RESID) {
-                            pre[i] = *reinterpret_cast<const float4*>(static_cast<const float*>(p.out0) + roff[i] + co);
-                        } else if (EPI == EPI_PATCH) {
-                            const int t = ry[i] * p.W + rx[i];
-                            pre[i] = *reinterpret_cast<const float4*>(p.vec1 + static_cast<size_t>(t) * p.ldo + co);
-                        } else if (EPI == EPI_DEC && p.skip != nullptr) {
-                            const uint2 u = *reinterpret_cast<const uint2*>(static_cast<const uint8_t*>(p.skip) + roff[i] + qoff);
-                            const float2 f0 = H::unpack(u.x), f1 = H::unpack(u.y);
-                            pre[i] = make_float4(f0.x, f0.y, f1.x, f1.y);
-                        }
-                    }
-                    // ---- phase 2: math + stores
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const int rl = 4 * i + sub;
-                        float4 a = scr[rl * 8 + (q4 ^ (rl & 7))];
-                        if (!ok[i]) continue;
-                        if (EPI == EPI_STORE16 || EPI == EPI_GELU16) {
-                            a.x += bias4.x; a.y += bias4.y; a.z += bias4.z; a.w += bias4.w;
-                            if (EPI == EPI_GELU16) { a.x = gelu_erf(a.x); a.y = gelu_erf(a.y); a.z = gelu_erf(a.z); a.w = gelu_erf(a.w); }
-                            uint2 pk;
-                            pk.x = H::pack(a.x, a.y); pk.y = H::pack(a.z, a.w);
-                            *reinterpret_cast<uint2*>(static_cast<typename H::T*>(p.out0) + roff[i] + co) = pk;
-                        } else if (EPI == EPI_RESID) {
-                            float4 x = pre[i];
-                            x.x += g4.x * (a.x + bias4.x); x.y += g4.y * (a.y + bias4.y);
-                            x.z += g4.z * (a.z + bias4.z); x.w += g4.w * (a.w + bias4.w);
-                            *reinterpret_cast<float4*>(static_cast<float*>(p.out0) + roff[i] + co) = x;
-                        } else if (EPI == EPI_PATCH) {
-                            *reinterpret_cast<float4*>(static_cast<float*>(p.out0) + roff[i] + co) =
-                                make_float4(a.x + pre[i].x, a.y + pre[i].y, a.z + pre[i].z, a.w + pre[i].w);
-                        } else if (EPI == EPI_DEC) {
-                            a.x += bias4.x + pre[i].x; a.y += bias4.y + pre[i].y; a.z += bias4.z + pre[i].z; a.w += bias4.w + pre[i].w;
-                            if (p.vec1 != nullptr) {
-                                const float uu = p.su * ((2 * sX[i] + 1) * inv_wo - 1.0f);
-                                const float vv = p.sv * ((2 * sY[i] + 1) * inv_ho - 1.0f);
-                                a.x += g4.x * uu + h4.x * vv; a.y += g4.y * uu + h4.y * vv;
-                                a.z += g4.z * uu + h4.z * vv; a.w += g4.w * uu + h4.w * vv;
-                            }
-                            const bool edge = (eflags[i] & qmask) != 0;
-                            if (p.out0 != nullptr) {
-                                uint2 pk;
-                                pk.x = H::pack(a.x, a.y); pk.y = H::pack(a.z, a.w);
-                                if (!edge) *reinterpret_cast<uint2*>(static_cast<uint8_t*>(p.out0) + roff[i] + qoff) = pk;
-                                else store_px_border8(static_cast<uint8_t*>(p.out0), rb[i], sY[i], sX[i], p.Ho, p.Wo, p.Hop, p.Wop, p.ldo, co, pk);
-                            }
-                            if (p.out1 != nullptr) {
-                                uint2 pk;
-                                pk.x = H::pack(fmaxf(a.x, 0.f), fmaxf(a.y, 0.f)); pk.y = H::pack(fmaxf(a.z, 0.f), fmaxf(a.w, 0.f));
-                                if (!edge) *reinterpret_cast<uint2*>(static_cast<uint8_t*>(p.out1) + roff[i] + qoff) = pk;
-                                else store_px_border8(static_cast<uint8_t*>(p.out1), rb[i], sY[i], sX[i], p.Ho, p.Wo, p.Hop, p.Wop, p.ldo, co, pk);
-                            }
-                        }
-                    }
-                    __syncwarp();
-                }
-            }
+            epilogue_tile<BN, Cfg::kColsPerWarp, AMODE, EPI, BF16>(p, mt, nt, t_addr, scr, quarter, lane, col_begin);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tempty[acc]);
