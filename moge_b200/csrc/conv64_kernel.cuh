@@ -15,15 +15,18 @@ template <int BN> struct Conv64Cfg {
     static constexpr int kABytes = 160 * 128;                       // box {64 ch, 16 px, 10 rows}
     static constexpr int kWBytes = BN * 128 * 10;                   // 9 taps + 1 aux block, each [BN][64] 128B-swizzled
     static constexpr int kStages = (BN >= 64) ? 5 : 6;
-    static constexpr int kEpiWarps = (BN >= 64) ? 8 : 4;
+    // 4 TMEM accumulator stages; the 8 epilogue warps form TWO groups of 4 (one warp per TMEM lane quarter) that drain
+    // alternate tiles concurrently, so the per-tile epilogue latency chain (TMEM load -> transpose -> global) overlaps.
+    static constexpr int kAccStages = 4;
+    static constexpr int kEpiWarps = 8;
     static constexpr int kThreads = 64 + 32 * kEpiWarps;
-    static constexpr int kTmemCols = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : 128;
+    static constexpr int kTmemCols = (kAccStages * BN <= 32) ? 32 : (kAccStages * BN <= 64) ? 64 : (kAccStages * BN <= 128) ? 128 : 256;
     static constexpr int kScratchBytes = kEpiWarps * 4096;
     static constexpr int kSmemBytes = kStages * kABytes + kWBytes + 1024 + 256 + kScratchBytes;
-    static constexpr int kColsPerWarp = (kEpiWarps == 8) ? BN / 2 : BN;
+    static constexpr int kColsPerWarp = BN;
 };
 
-template <int BN, int EPI, bool BF16>
+template <int BN, int EPI, bool BF16, int DF>
 __global__ void __launch_bounds__(Conv64Cfg<BN>::kThreads, 1)
 conv64_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapAux,
               const __grid_constant__ CUtensorMap mapW, const UmmaParams p) {
@@ -35,8 +38,8 @@ conv64_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
     uint64_t* full = reinterpret_cast<uint64_t*>(sW + Cfg::kWBytes);
     uint64_t* empty = full + S;
     uint64_t* tfull = empty + S;
-    uint64_t* tempty = tfull + 2;
-    uint64_t* wfull = tempty + 2;
+    uint64_t* tempty = tfull + Cfg::kAccStages;
+    uint64_t* wfull = tempty + Cfg::kAccStages;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wfull + 1);
     float* scratch_base = reinterpret_cast<float*>(sW + Cfg::kWBytes + 256);
 
@@ -51,7 +54,7 @@ conv64_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
         tma_prefetch_desc(&mapW);
         if (p.kb_aux) tma_prefetch_desc(&mapAux);
         for (int s = 0; s < S; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-        for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], Cfg::kEpiWarps); }
+        for (int a = 0; a < Cfg::kAccStages; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 4); }
         mbar_init(wfull, 1);
         fence_mbar_init();
     }
@@ -93,8 +96,8 @@ conv64_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
             int it = 0;
             const uint32_t w0 = smem_u32(sW);
             for (int mt = mt0; mt < p.num_m_tiles; mt += mstep, ++it) {
-                const int acc = it & 1;
-                mbar_wait(&tempty[acc], ((it >> 1) & 1) ^ 1);
+                const int acc = it % Cfg::kAccStages;
+                mbar_wait(&tempty[acc], ((it / Cfg::kAccStages) & 1) ^ 1);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * BN;
                 for (int i = 0; i < nstage; ++i) {
@@ -124,15 +127,15 @@ conv64_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
     } else {
         const int ew = warp - 2;
         const int quarter = warp & 3;
-        const int col_begin = (Cfg::kEpiWarps == 8) ? (ew >> 2) * (BN / 2) : 0;
+        const int group = ew >> 2;                     // epilogue group 0 drains even tiles, group 1 odd tiles
         float4* scr = reinterpret_cast<float4*>(scratch_base + ew * 1024);
-        int it = 0;
-        for (int mt = mt0; mt < p.num_m_tiles; mt += mstep, ++it) {
-            const int acc = it & 1;
-            mbar_wait(&tfull[acc], (it >> 1) & 1);
+        int it = group;
+        for (int mt = mt0 + group * mstep; mt < p.num_m_tiles; mt += 2 * mstep, it += 2) {
+            const int acc = it % Cfg::kAccStages;
+            mbar_wait(&tfull[acc], (it / Cfg::kAccStages) & 1);
             tc_fence_after();
-            const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN + col_begin;
-            epilogue_tile<BN, Cfg::kColsPerWarp, AMODE_TILES, EPI, BF16>(p, mt, nt, t_addr, scr, quarter, lane, col_begin);
+            const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN;
+            epilogue_tile<BN, Cfg::kColsPerWarp, AMODE_TILES, EPI, BF16, DF>(p, mt, nt, t_addr, scr, quarter, lane, 0);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tempty[acc]);

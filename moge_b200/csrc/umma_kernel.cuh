@@ -84,7 +84,7 @@ __device__ __forceinline__ void store_px_border(uint8_t* base, int b, int Y, int
 }
 
 // same for an 8-byte (4 x 16-bit) piece
-__device__ __forceinline__ void store_px_border8(uint8_t* base, int b, int Y, int X, int Ho, int Wo, int Hop, int Wop,
+static __device__ __noinline__ void store_px_border8(uint8_t* base, int b, int Y, int X, int Ho, int Wo, int Hop, int Wop,
                                                  int ld, int c0, uint2 q) {
     uint8_t* centre = base + (((static_cast<size_t>(b) * Hop + Y + 1) * Wop + X + 1) * ld + c0) * 2;
     *reinterpret_cast<uint2*>(centre) = q;
@@ -101,10 +101,19 @@ __device__ __forceinline__ void store_px_border8(uint8_t* base, int b, int Y, in
 // TMEM hands each thread one accumulator ROW; global memory wants warps on contiguous COLUMNS.  Every 32x32 chunk is
 // therefore transposed through a per-warp swizzled smem tile: afterwards 8 lanes x float4 cover the 32 columns of one
 // row and each warp instruction touches 4 rows (4 x 128 B), fully coalesced.
-template <int BN, int COLS, int AMODE, int EPI, bool BF16>
+// DF < 0: the EPI_DEC variant (raw / ReLU copies, skip, UV, pixel shuffle) is decided at run time from the params;
+// DF >= 0: compile-time bit mask (DF_RAW | DF_RELU | DF_SKIP | DF_UV | DF_SHUFFLE) -- a much smaller hot loop.
+enum : int { DF_RAW = 1, DF_RELU = 2, DF_SKIP = 4, DF_UV = 8, DF_SHUFFLE = 16 };
+
+template <int BN, int COLS, int AMODE, int EPI, bool BF16, int DF = -1>
 __device__ __forceinline__ void epilogue_tile(const UmmaParams& p, int mt, int nt, uint32_t t_addr, float4* scr, int quarter,
                                               int lane, int col_begin) {
     using H = H16<BF16>;
+    const bool has_raw = (DF < 0) ? (p.out0 != nullptr) : ((DF & DF_RAW) != 0);
+    const bool has_relu = (DF < 0) ? (p.out1 != nullptr) : ((DF & DF_RELU) != 0);
+    const bool has_skip = (DF < 0) ? (p.skip != nullptr) : ((DF & DF_SKIP) != 0);
+    const bool has_uv = (DF < 0) ? (p.vec1 != nullptr) : ((DF & DF_UV) != 0);
+    const bool shuffle = (DF < 0) ? (p.shuffle != 0) : ((DF & DF_SHUFFLE) != 0);
     const int row = quarter * 32 + lane;
     const int sub = lane >> 3;        // which of the 4 rows of a pass this lane serves
     const int q4 = lane & 7;          // which float4 (4 columns) of the 32-column chunk
@@ -152,6 +161,14 @@ __device__ __forceinline__ void epilogue_tile(const UmmaParams& p, int mt, int n
         __syncwarp();
     } else {
         // ---- coordinates of the 8 rows this lane serves after the transpose (row = 4*i + sub of the warp's 32)
+        int tile_b = 0, tile_y0 = 0, tile_x0 = 0;
+        if (AMODE == AMODE_TILES) {
+            const int per_img = p.tiles_x * p.tiles_y;
+            tile_b = mt / per_img;
+            const int r = mt % per_img;
+            tile_y0 = (r / p.tiles_x) * TILE_PH;
+            tile_x0 = (r % p.tiles_x) * TILE_PW;
+        }
         bool ok[8];
         int rb[8], ry[8], rx[8];
         size_t roff[8];      // element offset of the row (ROWS epilogues) / BYTE offset of the centre output pixel (EPI_DEC)
@@ -171,15 +188,13 @@ __device__ __forceinline__ void epilogue_tile(const UmmaParams& p, int mt, int n
                     if (EPI == EPI_PATCH) roff[i] = (static_cast<size_t>(rb[i]) * (p.T + 1) + 1 + t) * p.ldo;
                 }
             } else {
-                const int per_img = p.tiles_x * p.tiles_y;
-                rb[i] = mt / per_img;
-                const int r = mt % per_img;
-                ry[i] = (r / p.tiles_x) * TILE_PH + rl / TILE_PW;
-                rx[i] = (r % p.tiles_x) * TILE_PW + rl % TILE_PW;
+                rb[i] = tile_b;
+                ry[i] = tile_y0 + rl / TILE_PW;
+                rx[i] = tile_x0 + rl % TILE_PW;
                 ok[i] = (ry[i] < p.H) && (rx[i] < p.W);
             }
             if (EPI == EPI_DEC) {
-                const int sh = p.shuffle ? 2 : 1;
+                const int sh = shuffle ? 2 : 1;
                 roff[i] = ((static_cast<size_t>(rb[i]) * p.Hop + sh * ry[i] + 1) * p.Wop + sh * rx[i] + 1) * p.ldo * 2;
                 eflags[i] = (ry[i] == 0 ? 1 : 0) | (ry[i] == p.H - 1 ? 2 : 0) | (rx[i] == 0 ? 4 : 0) | (rx[i] == p.W - 1 ? 8 : 0);
             }
@@ -199,7 +214,7 @@ __device__ __forceinline__ void epilogue_tile(const UmmaParams& p, int mt, int n
             int qd = 0;
             size_t qoff = 0;                               // EPI_DEC: byte offset of this chunk relative to the centre pixel
             int qmask = 15;                                // which source-grid edges replicate for this chunk
-            if (EPI == EPI_DEC && p.shuffle) {
+            if (EPI == EPI_DEC && shuffle) {
                 qd = col / p.ldo;                          // ldo == C_out; a 32-column chunk never straddles qd
                 co -= qd * p.ldo;
                 qoff = (static_cast<size_t>(qd >> 1) * p.Wop + (qd & 1)) * p.ldo * 2;
@@ -209,7 +224,7 @@ __device__ __forceinline__ void epilogue_tile(const UmmaParams& p, int mt, int n
             float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f), g4 = bias4, h4 = bias4;
             if (EPI != EPI_PATCH) bias4 = *reinterpret_cast<const float4*>(p.bias + co);
             if (EPI == EPI_RESID) g4 = *reinterpret_cast<const float4*>(p.vec1 + co);
-            if (EPI == EPI_DEC && p.vec1 != nullptr) {
+            if (EPI == EPI_DEC && has_uv) {
                 g4 = *reinterpret_cast<const float4*>(p.vec1 + co);
                 h4 = *reinterpret_cast<const float4*>(p.vec2 + co);
             }
@@ -221,20 +236,22 @@ __device__ __forceinline__ void epilogue_tile(const UmmaParams& p, int mt, int n
             for (int i = 0; i < 8; ++i) {
                 pre[i] = make_float4(0.f, 0.f, 0.f, 0.f);
                 sY[i] = ry[i]; sX[i] = rx[i];
-                if (EPI == EPI_DEC && p.shuffle) { sY[i] = 2 * ry[i] + (qd >> 1); sX[i] = 2 * rx[i] + (qd & 1); }
+                if (EPI == EPI_DEC && shuffle) { sY[i] = 2 * ry[i] + (qd >> 1); sX[i] = 2 * rx[i] + (qd & 1); }
                 if (!ok[i]) continue;
                 if (EPI == EPI_RESID) {
                     pre[i] = *reinterpret_cast<const float4*>(static_cast<const float*>(p.out0) + roff[i] + co);
                 } else if (EPI == EPI_PATCH) {
                     const int t = ry[i] * p.W + rx[i];
                     pre[i] = *reinterpret_cast<const float4*>(p.vec1 + static_cast<size_t>(t) * p.ldo + co);
-                } else if (EPI == EPI_DEC && p.skip != nullptr) {
+                } else if (EPI == EPI_DEC && has_skip) {
                     const uint2 u = *reinterpret_cast<const uint2*>(static_cast<const uint8_t*>(p.skip) + roff[i] + qoff);
                     const float2 f0 = H::unpack(u.x), f1 = H::unpack(u.y);
                     pre[i] = make_float4(f0.x, f0.y, f1.x, f1.y);
                 }
             }
             // ---- phase 2: math + stores
+            uint2 pk_raw[8], pk_relu[8];
+            unsigned edge_rows = 0;
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 const int rl = 4 * i + sub;
@@ -256,26 +273,31 @@ __device__ __forceinline__ void epilogue_tile(const UmmaParams& p, int mt, int n
                         make_float4(a.x + pre[i].x, a.y + pre[i].y, a.z + pre[i].z, a.w + pre[i].w);
                 } else if (EPI == EPI_DEC) {
                     a.x += bias4.x + pre[i].x; a.y += bias4.y + pre[i].y; a.z += bias4.z + pre[i].z; a.w += bias4.w + pre[i].w;
-                    if (p.vec1 != nullptr) {
+                    if (has_uv) {
                         const float uu = p.su * ((2 * sX[i] + 1) * inv_wo - 1.0f);
                         const float vv = p.sv * ((2 * sY[i] + 1) * inv_ho - 1.0f);
                         a.x += g4.x * uu + h4.x * vv; a.y += g4.y * uu + h4.y * vv;
                         a.z += g4.z * uu + h4.z * vv; a.w += g4.w * uu + h4.w * vv;
                     }
-                    const bool edge = (eflags[i] & qmask) != 0;
-                    if (p.out0 != nullptr) {
-                        uint2 pk;
-                        pk.x = H::pack(a.x, a.y); pk.y = H::pack(a.z, a.w);
-                        if (!edge) *reinterpret_cast<uint2*>(static_cast<uint8_t*>(p.out0) + roff[i] + qoff) = pk;
-                        else store_px_border8(static_cast<uint8_t*>(p.out0), rb[i], sY[i], sX[i], p.Ho, p.Wo, p.Hop, p.Wop, p.ldo, co, pk);
+                    // centre pixel: straight-line predicated stores; the (rare) replicated-border copies are done after the loop
+                    if ((eflags[i] & qmask) != 0) edge_rows |= 1u << i;
+                    if (has_raw) {
+                        pk_raw[i].x = H::pack(a.x, a.y); pk_raw[i].y = H::pack(a.z, a.w);
+                        *reinterpret_cast<uint2*>(static_cast<uint8_t*>(p.out0) + roff[i] + qoff) = pk_raw[i];
                     }
-                    if (p.out1 != nullptr) {
-                        uint2 pk;
-                        pk.x = H::pack(fmaxf(a.x, 0.f), fmaxf(a.y, 0.f)); pk.y = H::pack(fmaxf(a.z, 0.f), fmaxf(a.w, 0.f));
-                        if (!edge) *reinterpret_cast<uint2*>(static_cast<uint8_t*>(p.out1) + roff[i] + qoff) = pk;
-                        else store_px_border8(static_cast<uint8_t*>(p.out1), rb[i], sY[i], sX[i], p.Ho, p.Wo, p.Hop, p.Wop, p.ldo, co, pk);
+                    if (has_relu) {
+                        pk_relu[i].x = H::pack(fmaxf(a.x, 0.f), fmaxf(a.y, 0.f)); pk_relu[i].y = H::pack(fmaxf(a.z, 0.f), fmaxf(a.w, 0.f));
+                        *reinterpret_cast<uint2*>(static_cast<uint8_t*>(p.out1) + roff[i] + qoff) = pk_relu[i];
                     }
                 }
+            }
+            if (EPI == EPI_DEC && edge_rows != 0) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+                    if (edge_rows >> i & 1) {
+                        if (has_raw) store_px_border8(static_cast<uint8_t*>(p.out0), rb[i], sY[i], sX[i], p.Ho, p.Wo, p.Hop, p.Wop, p.ldo, co, pk_raw[i]);
+                        if (has_relu) store_px_border8(static_cast<uint8_t*>(p.out1), rb[i], sY[i], sX[i], p.Ho, p.Wo, p.Hop, p.Wop, p.ldo, co, pk_relu[i]);
+                    }
             }
             __syncwarp();
         }
