@@ -87,6 +87,21 @@ class ClockSampler:
                 "reasons": reasons, "samples": len(self.rows)}
 
 
+def host_threads():
+    """Host cores this process may actually use (affinity / cgroup aware), not the machine total."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except Exception:
+        n = os.cpu_count() or 1
+    try:
+        q = open("/sys/fs/cgroup/cpu.max").read().split()
+        if q[0] != "max":
+            n = max(1, min(n, int(int(q[0]) / int(q[1]))))
+    except Exception:
+        pass
+    return n
+
+
 def cpu_port_images_per_s(size, res, tokens, n_images, threads):
     """The reference algorithm (oracle port, fp32) on the host cores: images/s over `n_images` single-image infers."""
     from moge_b200.configs import model_config
@@ -114,7 +129,7 @@ def run_reference(a):
     if rank != 0:
         return
     from moge_b200.configs import token_grid
-    threads = os.cpu_count() or 1
+    threads = host_threads()
     h, w = token_grid(a.res, a.res, a.tokens)
     per_step = 1
     for _ in range(max(a.warmup - 2, 0) if a.warmup > 2 else 0):
@@ -148,6 +163,7 @@ def run_engine(a):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG", "WARN")          # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=dev)
     cfg = model_config(a.size, True)
     # ---- weights: rank 0 builds the seeded checkpoint; one NCCL broadcast ships it to every GPU
@@ -219,6 +235,7 @@ def run_engine(a):
     if world > 1:
         o = model.infer(dev_in, num_tokens=a.tokens)
         counts = [B] * world
+        parallel.gather_outputs(o, counts)                     # first call sets up the P2P channels
         ms_g = timed(lambda: parallel.gather_outputs(o, counts), 1)
         gather = {"ms": ms_g, "bytes_to_rank0": d2h_bytes * (world - 1)}
 
@@ -275,7 +292,7 @@ def run_engine(a):
 
     cpu = None
     if world == 1 and not a.no_cpu_baseline:
-        threads = os.cpu_count() or 1
+        threads = host_threads()
         ips, dt = cpu_port_images_per_s(a.size, R, a.tokens, a.cpu_images, threads)
         cpu = {"value": ips, "unit": "images/s", "cores": threads, "kind": "port",
                "sample": f"{a.cpu_images} single-image infer() calls ({dt:.1f} s), oracle/moge_port.py fp32, torch CPU {threads} threads"}

@@ -51,6 +51,11 @@ __global__ void preprocess_kernel(const void* __restrict__ image, int dtype, int
             const int c = k / 196, py = (k % 196) / 14, px = k % 14;
             const int Y = (t / w) * 14 + py, X = (t % w) * 14 + px;
             const int OH = h * 14, OW = w * 14;
+            const size_t plane0 = (static_cast<size_t>(b) * 3 + c) * H * W;
+            if (H == OH && W == OW) {                         // native grid (e.g. 518 px @ 37x37): the resize is the identity
+                patches[idx] = H16<BF16>::from_float((load_img(image, dtype, plane0 + static_cast<size_t>(Y) * W + X) - mean[c]) / stdv[c]);
+                continue;
+            }
             float cy, cx;
             const AAFilter fy = aa_setup(H, OH, Y, cy);
             const AAFilter fx = aa_setup(W, OW, X, cx);

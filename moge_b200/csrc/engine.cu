@@ -11,6 +11,7 @@
 #include <string>
 #include <vector>
 #include <math.h>
+#include <stdlib.h>
 
 namespace mg {
 
@@ -82,6 +83,11 @@ struct Plan {
     // output bindings (set per forward)
     float* points = nullptr; float* normal = nullptr; float* mask = nullptr; float* scale = nullptr;
     const void* image = nullptr; int image_dtype = 0;
+    // CUDA graphs of the launch list, one per distinct binding of the caller's pointers (the launch list of a
+    // single image is ~240 kernels of a few microseconds each: replaying a graph removes the per-launch CPU cost)
+    struct GraphEntry { const void* key[6]; int dtype; cudaGraphExec_t exec; };
+    std::vector<GraphEntry> graphs;
+    int eager_runs = 0;
 };
 
 }  // namespace mg
@@ -104,6 +110,9 @@ struct moge_engine {
     std::vector<const float*> mlp_w, mlp_b;
     std::vector<std::unique_ptr<Plan>> plans;
     Plan* last_plan = nullptr;
+    bool use_graphs = true;
+    cudaStream_t own_stream = nullptr;
+    cudaEvent_t ev_in = nullptr, ev_out = nullptr;
 
     int alloc(void** p, size_t bytes) {
         CUDA_TRY(cudaMalloc(p, bytes ? bytes : 16));
@@ -694,7 +703,11 @@ static int get_plan(moge_engine* e, int B, int H, int W, int h, int w, void* ws,
             *out = p.get();
             return 0;
         }
-    if (e->plans.size() >= 16) { if (e->last_plan == e->plans.front().get()) e->last_plan = nullptr; e->plans.erase(e->plans.begin()); }
+    if (e->plans.size() >= 16) {
+        if (e->last_plan == e->plans.front().get()) e->last_plan = nullptr;
+        for (auto& g : e->plans.front()->graphs) cudaGraphExecDestroy(g.exec);
+        e->plans.erase(e->plans.begin());
+    }
     std::unique_ptr<Plan> pl(new Plan());
     pl->B = B; pl->H = H; pl->W = W; pl->h = h; pl->w = w; pl->ws = ws; pl->ws_bytes = ws_bytes;
     const int D = e->cfg.embed_dim;
@@ -746,6 +759,14 @@ int moge_engine_create(const moge_config_t* cfg, int device, moge_engine_t** out
     if (prop.major != 10) return set_error("device %d is sm_%d%d; libmoge_b200 contains sm_100a code only", device, prop.major, prop.minor);
     moge_engine* e = new moge_engine();
     e->cfg = *cfg; e->device = device; e->num_sms = prop.multiProcessorCount; e->bf16 = cfg->compute_dtype == MOGE_BF16;
+    const char* env = getenv("MOGE_B200_GRAPHS");
+    e->use_graphs = !(env && env[0] == '0');
+    if (cudaStreamCreateWithFlags(&e->own_stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&e->ev_in, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&e->ev_out, cudaEventDisableTiming) != cudaSuccess) {
+        delete e;
+        return set_error("stream/event creation failed");
+    }
     *out = e;
     return 0;
 }
@@ -754,6 +775,11 @@ void moge_engine_destroy(moge_engine_t* e) {
     if (!e) return;
     cudaSetDevice(e->device);
     cudaDeviceSynchronize();
+    for (auto& pl : e->plans)
+        for (auto& g : pl->graphs) cudaGraphExecDestroy(g.exec);
+    if (e->own_stream) cudaStreamDestroy(e->own_stream);
+    if (e->ev_in) cudaEventDestroy(e->ev_in);
+    if (e->ev_out) cudaEventDestroy(e->ev_out);
     for (void* p : e->owned) cudaFree(p);
     for (auto& kv : e->raw) if (kv.second.p) cudaFree(kv.second.p);
     delete e;
@@ -810,7 +836,44 @@ int moge_engine_forward(moge_engine_t* e, const void* image, int image_dtype, in
     pl->image = image; pl->image_dtype = image_dtype;
     pl->points = points; pl->normal = normal; pl->mask = mask_prob; pl->scale = metric_scale;
     e->last_plan = pl;
-    for (auto& op : pl->ops) MG_TRY(op.fn(st));
+    // ---- graph replay (small batches only: at large batch the GPU is the bottleneck and the CPU runs ahead anyway)
+    const bool want_graph = e->use_graphs && static_cast<long>(B) * h * w <= 4 * 3600;
+    if (!want_graph || pl->eager_runs == 0) {          // the first run of a plan is eager (sets kernel attributes, warms caches)
+        pl->eager_runs++;
+        for (auto& op : pl->ops) MG_TRY(op.fn(st));
+        return 0;
+    }
+    const void* key[6] = {image, points, normal, mask_prob, metric_scale, workspace};
+    cudaGraphExec_t exec = nullptr;
+    for (auto& g : pl->graphs)
+        if (g.dtype == image_dtype && std::equal(key, key + 6, g.key)) exec = g.exec;
+    // stream capture is not allowed on the legacy default stream: run on the engine's own stream, fenced by events
+    const bool legacy = (st == nullptr || st == cudaStreamLegacy || st == cudaStreamPerThread);
+    cudaStream_t run = legacy ? e->own_stream : st;
+    if (legacy) {
+        CUDA_TRY(cudaEventRecord(e->ev_in, st));
+        CUDA_TRY(cudaStreamWaitEvent(e->own_stream, e->ev_in, 0));
+    }
+    if (!exec) {
+        cudaGraph_t graph = nullptr;
+        CUDA_TRY(cudaStreamBeginCapture(run, cudaStreamCaptureModeThreadLocal));
+        int rc = 0;
+        for (auto& op : pl->ops) { rc = op.fn(run); if (rc) break; }
+        cudaError_t ce = cudaStreamEndCapture(run, &graph);
+        if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+        if (ce != cudaSuccess) return set_error("graph capture failed: %s", cudaGetErrorString(ce));
+        CUDA_TRY(cudaGraphInstantiate(&exec, graph, 0));
+        cudaGraphDestroy(graph);
+        if (pl->graphs.size() >= 8) { cudaGraphExecDestroy(pl->graphs.front().exec); pl->graphs.erase(pl->graphs.begin()); }
+        Plan::GraphEntry ge;
+        std::copy(key, key + 6, ge.key); ge.dtype = image_dtype; ge.exec = exec;
+        pl->graphs.push_back(ge);
+    }
+    CUDA_TRY(cudaGraphLaunch(exec, run));
+    if (legacy) {
+        CUDA_TRY(cudaEventRecord(e->ev_out, e->own_stream));
+        CUDA_TRY(cudaStreamWaitEvent(st, e->ev_out, 0));
+    }
     return 0;
 }
 

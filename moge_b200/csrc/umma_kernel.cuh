@@ -68,6 +68,8 @@ template <int BN> struct UmmaCfg {
     static constexpr int kColsPerWarp = (kEpiWarps == 8) ? BN / 2 : BN;
 };
 
+// Exact-erf GELU (nn.GELU() default, vision_transformer.py:61).  libdevice erff is FMA-pipe only; an A&S 7.1.26 variant
+// (MUFU.RCP + MUFU.EX2) was measured 25 % SLOWER here: the quarter-rate MUFU pipe becomes the epilogue bottleneck.
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
 
 // 64-byte (32 x 16-bit) store of one pixel's channel chunk into a padded NHWC buffer, replicating into the 1-pixel
