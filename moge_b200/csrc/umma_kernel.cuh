@@ -68,9 +68,21 @@ template <int BN> struct UmmaCfg {
     static constexpr int kColsPerWarp = (kEpiWarps == 8) ? BN / 2 : BN;
 };
 
-// Exact-erf GELU (nn.GELU() default, vision_transformer.py:61).  libdevice erff is FMA-pipe only; an A&S 7.1.26 variant
-// (MUFU.RCP + MUFU.EX2) was measured 25 % SLOWER here: the quarter-rate MUFU pipe becomes the epilogue bottleneck.
-__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+// Exact-erf GELU (nn.GELU() default, vision_transformer.py:61): gelu(x) = relu(x) - 0.5 |x| erfc(|x|/sqrt2), with
+// erfc(|x|/sqrt2) = 2^q(|x|), q a degree-5 fit of log2(erfc) on [0,6] (weighted for the GELU error; max |gelu error|
+// 7e-7 in fp32, far below the 16-bit output rounding).  5 FMA + 1 MUFU.EX2 + 4 other instructions instead of libdevice
+// erff's ~25: the fc1 epilogue is ALU-issue-bound, this is what keeps the tensor pipe fed.  (An A&S 7.1.26 variant with
+// MUFU.RCP + MUFU.EX2 was measured 25 % slower than erff: two quarter-rate MUFU ops per element are too many.)
+__device__ __forceinline__ float gelu_erf(float x) {
+    const float ax = fminf(fabsf(x), 6.0f);
+    float q = fmaf(-4.804994387e-04f, ax, 7.133518346e-03f);
+    q = fmaf(q, ax, -5.194617063e-02f);
+    q = fmaf(q, ax, -4.598676562e-01f);
+    q = fmaf(q, ax, -1.150842190e+00f);
+    q = fmaf(q, ax, -3.041332639e-05f);
+    const float t = fabsf(x) * ex2_approx(q);
+    return fmaf(-0.5f, t, fmaxf(x, 0.0f));
+}
 
 // 64-byte (32 x 16-bit) store of one pixel's channel chunk into a padded NHWC buffer, replicating into the 1-pixel
 // border when the pixel lies on the image edge (so that 3x3 taps of the consumer never need clamping).
