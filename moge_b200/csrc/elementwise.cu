@@ -398,39 +398,51 @@ __device__ __forceinline__ double block_sum(double v, double* red) {
 
 struct FsEval { double cost, jtr, jtj, focal; };
 
-// cost(s) = sum |f q - uv|^2 with q = xy/(z+s); derivative terms for the Gauss-Newton step on s.
-__device__ FsEval fs_eval(double s, const float* x, const float* y, const float* z, const float* u, const float* v,
+// Residuals r(s) = f(s) q - uv with q = xy/(z+s) (f in closed form or given).  Returns cost = |r(s)|^2 and, when
+// `with_jac`, J^T r and J^T J for the forward-difference Jacobian J = (r(s+h) - r(s)) / h the reference's solver uses
+// (SciPy's 2-point step): near the poles z + s = 0 of ill-posed maps the analytic and
+// the finite-difference Jacobians differ a lot, and parity with the reference means following ITS iterates.
+__device__ FsEval fs_eval(double s, bool with_jac, const float* x, const float* y, const float* z, const float* u, const float* v,
                           unsigned valid, bool fixed_focal, double focal_given, double* red) {
-    double a = 0, bq = 0, da = 0, dbq = 0;
+    // SciPy >= 1.x drives MINPACK lmder with its own 2-point Jacobian: h = sqrt(eps) * sign(s) * max(1, |s|)
+    const double h = 1.4901161193847656e-08 * (s < 0.0 ? -1.0 : 1.0) * fmax(1.0, fabs(s));
+    const double s2 = s + h;
+    double a = 0, bq = 0, a2 = 0, bq2 = 0;
 #pragma unroll
     for (int i = 0; i < FS_PER_THREAD; ++i)
         if (valid >> i & 1) {
             const double inv = 1.0 / (static_cast<double>(z[i]) + s);
             const double qx = x[i] * inv, qy = y[i] * inv;
-            const double dqx = -qx * inv, dqy = -qy * inv;
             a += qx * u[i] + qy * v[i];
             bq += qx * qx + qy * qy;
-            da += dqx * u[i] + dqy * v[i];
-            dbq += 2.0 * (qx * dqx + qy * dqy);
+            if (with_jac) {
+                const double inv2 = 1.0 / (static_cast<double>(z[i]) + s2);
+                const double px = x[i] * inv2, py = y[i] * inv2;
+                a2 += px * u[i] + py * v[i];
+                bq2 += px * px + py * py;
+            }
         }
-    a = block_sum(a, red); bq = block_sum(bq, red); da = block_sum(da, red); dbq = block_sum(dbq, red);
-    double f, df;
-    if (fixed_focal) { f = focal_given; df = 0.0; }
-    else { f = a / bq; df = (da * bq - a * dbq) / (bq * bq); }
+    a = block_sum(a, red); bq = block_sum(bq, red);
+    if (with_jac) { a2 = block_sum(a2, red); bq2 = block_sum(bq2, red); }
+    const double f = fixed_focal ? focal_given : a / bq;
+    const double f2 = fixed_focal ? focal_given : (with_jac ? a2 / bq2 : 0.0);
     double cost = 0, jtr = 0, jtj = 0;
 #pragma unroll
     for (int i = 0; i < FS_PER_THREAD; ++i)
         if (valid >> i & 1) {
             const double inv = 1.0 / (static_cast<double>(z[i]) + s);
-            const double qx = x[i] * inv, qy = y[i] * inv;
-            const double rx = f * qx - u[i], ry = f * qy - v[i];
-            const double jx = df * qx - f * qx * inv, jy = df * qy - f * qy * inv;
+            const double rx = f * x[i] * inv - u[i], ry = f * y[i] * inv - v[i];
             cost += rx * rx + ry * ry;
-            jtr += jx * rx + jy * ry;
-            jtj += jx * jx + jy * jy;
+            if (with_jac) {
+                const double inv2 = 1.0 / (static_cast<double>(z[i]) + s2);
+                const double jx = ((f2 * x[i] * inv2 - u[i]) - rx) / h, jy = ((f2 * y[i] * inv2 - v[i]) - ry) / h;
+                jtr += jx * rx + jy * ry;
+                jtj += jx * jx + jy * jy;
+            }
         }
     FsEval e;
-    e.cost = block_sum(cost, red); e.jtr = block_sum(jtr, red); e.jtj = block_sum(jtj, red); e.focal = f;
+    e.cost = block_sum(cost, red); e.focal = f; e.jtr = 0; e.jtj = 0;
+    if (with_jac) { e.jtr = block_sum(jtr, red); e.jtj = block_sum(jtj, red); }
     return e;
 }
 
@@ -472,16 +484,21 @@ focal_shift_kernel(const float* __restrict__ points, const float* __restrict__ m
     }
     // ---- MINPACK lmdif restated for one unknown (what scipy.optimize.least_squares(method='lm', x0=0, ftol=1e-3,
     // xtol=gtol=1e-8, x_scale=1 -> diag=1 (mode 2), factor=100) executes in the reference, geometry_numpy.py:90,109),
-    // with the analytic Jacobian in place of the forward difference.  Reproducing its trust-region updates and its
+    // including its forward-difference Jacobian (fdjac2).  Reproducing its trust-region updates and its
     // ftol stopping rule -- not just its fixed point -- keeps parity with the reference on ill-posed maps as well.
     const double ftol = 1e-3, xtol = 1e-8, gtol = 1e-8, epsmch = 2.220446049250313e-16, dwarf = 2.2250738585072014e-308;
     double s = 0.0;
-    FsEval cur = fs_eval(s, x, y, z, u, v, valid, fixed, fgiven, red);
+    FsEval cur = fs_eval(s, true, x, y, z, u, v, valid, fixed, fgiven, red);
     double fnorm = sqrt(cur.cost);
     double par = 0.0, delta = 0.0, xnorm = 0.0;
     int nfev = 1;
     bool stop = false;
+    bool jac_stale = false;
     for (int iter = 1; !stop && nfev < 200; ++iter) {
+        if (jac_stale) {                                  // lmdif: Jacobian re-evaluated at the start of every outer iteration
+            cur = fs_eval(s, true, x, y, z, u, v, valid, fixed, fgiven, red);
+            jac_stale = false;
+        }
         const double jtj = cur.jtj, jtr = cur.jtr;
         const double jnorm = sqrt(jtj);
         if (iter == 1) {
@@ -526,7 +543,7 @@ focal_shift_kernel(const float* __restrict__ points, const float* __restrict__ m
             const double pstep = -xs;
             const double pnorm = fabs(pstep);
             if (iter == 1) delta = fmin(delta, pnorm);
-            const FsEval nxt = fs_eval(s + pstep, x, y, z, u, v, valid, fixed, fgiven, red);
+            FsEval nxt = fs_eval(s + pstep, false, x, y, z, u, v, valid, fixed, fgiven, red);
             ++nfev;
             const double fnorm1 = sqrt(nxt.cost);
             double actred = -1.0;
@@ -547,6 +564,7 @@ focal_shift_kernel(const float* __restrict__ points, const float* __restrict__ m
             if (ratio >= 1e-4) {                                    // successful iteration
                 s += pstep;
                 cur = nxt;
+                jac_stale = true;
                 xnorm = fabs(s);
                 fnorm = fnorm1;
             }
@@ -564,7 +582,7 @@ focal_shift_kernel(const float* __restrict__ points, const float* __restrict__ m
     }
     // ... and recomputes the focal with the float32 shift (geometry_numpy.py:93-94)
     if (!fixed) {
-        const FsEval fin = fs_eval(static_cast<double>(static_cast<float>(s)), x, y, z, u, v, valid, false, 0.0, red);
+        const FsEval fin = fs_eval(static_cast<double>(static_cast<float>(s)), false, x, y, z, u, v, valid, false, 0.0, red);
         if (threadIdx.x == 0) focal_out[b] = static_cast<float>(fin.focal);
     }
 }

@@ -455,6 +455,18 @@ static int add_conv(moge_engine* e, Plan* pl, const ConvW& cw, const void* src, 
     // C_in = 64 3x3 convs (levels 3/4): resident weights + one halo box per horizontal tap (conv64_kernel.cuh)
     const bool use64 = cw.taps == 9 && cw.cin == 64 && (cw.caux == 0 || cw.caux == 64) && gs.Hp >= 10 &&
                        ((epi == EPI_HEADOUT && cw.N == 16) || (epi == EPI_DEC && cw.N % 64 == 0));
+    const bool use_s = use64 && epi == EPI_DEC && gs.Hp >= 18 && getenv("MOGE_B200_CONVS") != nullptr;
+    if (use_s) {       // swapped operands: M = 64 output channels, N = 256 pixels (convs_kernel.cuh)
+        p.tiles_x = (gs.W + 15) / 16; p.tiles_y = (gs.H + 15) / 16;
+        p.num_m_tiles = B * p.tiles_x * p.tiles_y;
+        p.num_n_tiles = cw.N / 64;
+        MG_TRY(make_map_nhwc(&ma, src, cw.cin, gs.Wp, gs.Hp, B, 18));
+        if (cw.caux) MG_TRY(make_map_nhwc(&mx, aux, cw.caux, gs.Wp, gs.Hp, B, 16));
+        else mx = ma;
+        MG_TRY(make_map_2d(&mb, cw.w, cw.Ktot, cw.N, cw.Ktot, 64));
+        pl->ops.add([=](cudaStream_t st) { return launch_convs(epi, bf16, ma, mx, mb, p, sms, st); }, name, flops, bytes);
+        return 0;
+    }
     if (use64) {
         const int bn64 = (epi == EPI_HEADOUT) ? 16 : 64;
         p.num_n_tiles = cw.N / bn64;
@@ -989,7 +1001,14 @@ int moge_op_conv(const void* x, const float* w, const float* bias, const void* s
         p.out0 = out_raw; p.out1 = out_relu; p.bias = bias; p.skip = skip; p.ldo = Cout;
         p.Ho = go.H; p.Wo = go.W; p.Hop = go.Hp; p.Wop = go.Wp; p.shuffle = shuffle;
         CUtensorMap ma, mb;
-        if (taps == 9 && Cin == 64 && N % 64 == 0 && gs.Hp >= 10) {
+        if (taps == 9 && Cin == 64 && N % 64 == 0 && gs.Hp >= 18 && getenv("MOGE_B200_CONVS") != nullptr) {
+            p.tiles_x = (W + 15) / 16; p.tiles_y = (H + 15) / 16;
+            p.num_m_tiles = B * p.tiles_x * p.tiles_y;
+            p.num_n_tiles = N / 64;
+            rc = make_map_nhwc(&ma, x, Cin, gs.Wp, gs.Hp, B, 18);
+            if (rc == 0) rc = make_map_2d(&mb, wp, Ktot, N, Ktot, 64);
+            if (rc == 0) rc = launch_convs(EPI_DEC, bf16, ma, ma, mb, p, dev_sms(), st);
+        } else if (taps == 9 && Cin == 64 && N % 64 == 0 && gs.Hp >= 10) {
             p.num_n_tiles = N / 64;
             rc = make_map_nhwc(&ma, x, Cin, gs.Wp, gs.Hp, B, 10);
             if (rc == 0) rc = make_map_2d(&mb, wp, Ktot, N, Ktot, 64);

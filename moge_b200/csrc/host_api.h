@@ -38,6 +38,10 @@ int launch_umma(int bn, int amode, int epi, bool bf16, const CUtensorMap& a, con
 int launch_conv64(int bn, int epi, bool bf16, const CUtensorMap& a, const CUtensorMap& aux, const CUtensorMap& w, const UmmaParams& p,
                   int num_sms, cudaStream_t st);
 
+// 3x3 conv with C_in = 64, operands swapped (weights on M = 64, 16x16 pixels on N = 256): convs_kernel.cuh
+int launch_convs(int epi, bool bf16, const CUtensorMap& a, const CUtensorMap& aux, const CUtensorMap& w, const UmmaParams& p, int num_sms,
+                 cudaStream_t st);
+
 int launch_attention(const CUtensorMap& mapQKV, void* out, int B, int N, int D, int heads, bool bf16, cudaStream_t st);
 
 // ---- small kernels (elementwise.cu)

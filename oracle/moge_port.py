@@ -228,11 +228,15 @@ def recover_focal_shift(points: torch.Tensor, mask: Optional[torch.Tensor] = Non
 
 
 def postprocess(points: torch.Tensor, normal, mask, metric_scale, aspect: float, fov_x=None,
-                force_projection: bool = True, apply_mask: bool = True) -> Dict[str, torch.Tensor]:
-    """v2.py:246-298 on raw forward() outputs (all fp32).  Batched; no squeeze."""
+                force_projection: bool = True, apply_mask: bool = True, focal_shift=None) -> Dict[str, torch.Tensor]:
+    """v2.py:246-298 on raw forward() outputs (all fp32).  Batched; no squeeze.
+    `focal_shift=(focal, shift)` injects a given solution of the focal/shift solve (test cut point for the
+    post-processing chain alone); by default it is solved here with SciPy like the reference."""
     points = points.clone().float()
     mask_b = None if mask is None else mask.float() > 0.5
-    if fov_x is None:
+    if focal_shift is not None:
+        focal, shift = focal_shift
+    elif fov_x is None:
         focal, shift = recover_focal_shift(points, mask_b)
     else:
         focal = aspect / (1 + aspect ** 2) ** 0.5 / torch.tan(torch.deg2rad(torch.as_tensor(fov_x, dtype=points.dtype) / 2))

@@ -92,7 +92,8 @@ def test_attention(B, N, heads, dtype):
 
 
 @pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
-@pytest.mark.parametrize("B,H,W,Cin,Cout", [(1, 18, 26, 64, 64), (2, 24, 40, 256, 256), (1, 37, 37, 128, 128), (1, 48, 36, 64, 32)])
+@pytest.mark.parametrize("B,H,W,Cin,Cout", [(1, 18, 26, 64, 64), (2, 24, 40, 256, 256), (1, 37, 37, 128, 128), (1, 48, 36, 64, 32),
+                                               (2, 40, 50, 64, 64), (1, 33, 47, 64, 128), (1, 9, 20, 64, 64)])
 def test_conv3x3_replicate_skip_relu(B, H, W, Cin, Cout, dtype):
     g = torch.Generator(device="cpu").manual_seed(H * W + Cin)
     x = torch.randn(B, Cin, H, W, generator=g).to(DEV).to(dtype)
@@ -109,6 +110,14 @@ def test_conv3x3_replicate_skip_relu(B, H, W, Cin, Cout, dtype):
     assert rel_l2(from_padded_nhwc(raw, H, W), ref) < TOL[dtype]
     assert rel_l2(from_padded_nhwc(relu, H, W), F.relu(ref)) < TOL[dtype]
     assert border_ok(raw, H, W) and border_ok(relu, H, W)
+
+
+def test_conv3x3_swapped_operands(monkeypatch):
+    """Experimental convs_kernel (weights on the M side, 16x16 pixels on N = 256), enabled by MOGE_B200_CONVS=1."""
+    monkeypatch.setenv("MOGE_B200_CONVS", "1")
+    for dtype in (torch.float16, torch.bfloat16):
+        test_conv3x3_replicate_skip_relu(2, 40, 50, 64, 64, dtype)
+        test_conv3x3_replicate_skip_relu(1, 33, 47, 64, 128, dtype)
 
 
 @pytest.mark.parametrize("dtype", [torch.float16])
