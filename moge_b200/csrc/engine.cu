@@ -490,8 +490,10 @@ static int add_linear(moge_engine* e, Plan* pl, const void* A, int M, int K, int
     UmmaParams p{};
     p.M = M; p.N = N; p.ntaps = 1; p.kb_main = (K + 63) / 64; p.kb_aux = 0;
     p.num_m_tiles = (M + TILE_M - 1) / TILE_M;
-    const int bn = pick_bn(N, {256, 128});
+    int bn = pick_bn(N, {256, 128});
     if (!bn) return set_error("linear: N=%d must be a multiple of 128", N);
+    // small batches: when 128x256 tiles cannot fill the SMs, halve the tile width (N = 128 MMAs still run at N/2 cycles)
+    if (bn == 256 && p.num_m_tiles * (N / 256) * 4 < e->num_sms * 3) bn = 128;
     p.num_n_tiles = N / bn;
     p.out0 = out; p.bias = bias; p.vec1 = v1; p.ldo = ldo; p.T = T; p.W = gridw;
     CUtensorMap ma, mb;

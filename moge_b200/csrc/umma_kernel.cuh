@@ -26,6 +26,9 @@ enum : int {
                        //        + folded 1x1 of the high-res neck map -> fp32 maps at the high resolution
 };
 
+#ifndef MG_STAGES256
+#define MG_STAGES256 4
+#endif
 constexpr int TILE_M = 128;
 constexpr int TILE_K = 64;     // 64 x 16-bit = one 128-byte swizzle row
 constexpr int TILE_PW = 16;    // pixel tile = 8 rows x 16 columns
@@ -59,7 +62,7 @@ struct UmmaParams {
 
 template <int BN> struct UmmaCfg {
     static constexpr int kStageBytes = TILE_M * 128 + BN * 128;
-    static constexpr int kStages = (BN >= 256) ? 4 : (BN >= 128) ? 6 : 8;
+    static constexpr int kStages = (BN >= 256) ? MG_STAGES256 : (BN >= 128) ? 6 : 8;
     static constexpr int kEpiWarps = (BN >= 64) ? 8 : 4;
     static constexpr int kThreads = 64 + 32 * kEpiWarps;
     static constexpr int kTmemCols = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
