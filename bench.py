@@ -160,10 +160,13 @@ def run_engine(a):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    # stdout carries exactly ONE JSON line: anything native libraries print (e.g. NCCL's version banner) goes to stderr
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        os.environ.setdefault("NCCL_DEBUG", "WARN")          # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=dev)
     cfg = model_config(a.size, True)
     # ---- weights: rank 0 builds the seeded checkpoint; one NCCL broadcast ships it to every GPU
@@ -318,7 +321,9 @@ def run_engine(a):
     }
     if gather:
         line["gather"] = gather
-    print(json.dumps(line))
+    sys.stdout.flush()
+    os.dup2(saved_stdout, 1)
+    print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
 
