@@ -1,5 +1,5 @@
 // HBM-bound kernels around the tensor-core path: input resize/normalise/patchify, pos-embed resampling, LayerNorm,
-// scale-head MLP, bilinear x2 upsample, fused output resize + remap, focal/shift recovery, post-processing.
+// scale-head MLP, fused output resize + remap, focal/shift recovery, post-processing.
 // Each kernel cites the reference lines it restates (paths relative to /root/reference).
 #include "common.cuh"
 #include "host_api.h"
@@ -262,62 +262,6 @@ int launch_scale_head(const float* cls, const float* const* w, const float* cons
         mlp_layer_kernel<<<grid, 256, 0, st>>>(cur, w[l], bias[l], dst, dims[l], dims[l + 1], last ? 0 : 1, last ? 1 : 0);
         cur = dst;
     }
-    CUDA_TRY(cudaGetLastError());
-    return 0;
-}
-
-// ------------------------------------------------------------------------------------------ bilinear x2
-// moge/model/modules.py:157 nn.Upsample(scale_factor=2, mode='bilinear', align_corners=False) on padded NHWC,
-// writing the interior and the replicated 1-pixel border of the destination.
-template <bool BF16>
-__global__ void upsample2x_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, int B, int H, int W, int Hp,
-                                  int Wp, int Hop, int Wop, int C) {
-    using Hh = H16<BF16>;
-    const int Ho = 2 * H, Wo = 2 * W, cv = C / 8;
-    const size_t total = static_cast<size_t>(B) * Ho * Wo * cv;
-    for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < total;
-         idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
-        const int c8 = static_cast<int>(idx % cv);
-        size_t r = idx / cv;
-        const int X = static_cast<int>(r % Wo); r /= Wo;
-        const int Y = static_cast<int>(r % Ho);
-        const int b = static_cast<int>(r / Ho);
-        const float sy = fmaxf((Y + 0.5f) * 0.5f - 0.5f, 0.f), sx = fmaxf((X + 0.5f) * 0.5f - 0.5f, 0.f);
-        const int y0 = static_cast<int>(sy), x0 = static_cast<int>(sx);
-        const int y1 = min(y0 + 1, H - 1), x1 = min(x0 + 1, W - 1);
-        const float ly = sy - y0, lx = sx - x0;
-        auto ld = [&](int y, int x) {
-            return *reinterpret_cast<const uint4*>(src + (((static_cast<size_t>(b) * Hp + y + 1) * Wp + x + 1) * C + c8 * 8) * 2);
-        };
-        const uint4 q00 = ld(y0, x0), q01 = ld(y0, x1), q10 = ld(y1, x0), q11 = ld(y1, x1);
-        const uint32_t* a = reinterpret_cast<const uint32_t*>(&q00);
-        const uint32_t* bq = reinterpret_cast<const uint32_t*>(&q01);
-        const uint32_t* c = reinterpret_cast<const uint32_t*>(&q10);
-        const uint32_t* d = reinterpret_cast<const uint32_t*>(&q11);
-        uint4 o;
-        uint32_t* ow = reinterpret_cast<uint32_t*>(&o);
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-            const float2 f00 = Hh::unpack(a[e]), f01 = Hh::unpack(bq[e]), f10 = Hh::unpack(c[e]), f11 = Hh::unpack(d[e]);
-            const float r0 = (1.f - ly) * ((1.f - lx) * f00.x + lx * f01.x) + ly * ((1.f - lx) * f10.x + lx * f11.x);
-            const float r1 = (1.f - ly) * ((1.f - lx) * f00.y + lx * f01.y) + ly * ((1.f - lx) * f10.y + lx * f11.y);
-            ow[e] = Hh::pack(r0, r1);
-        }
-        const int ya = (Y == 0) ? 0 : Y + 1, yb = (Y == Ho - 1) ? Y + 2 : Y + 1;
-        const int xa = (X == 0) ? 0 : X + 1, xb = (X == Wo - 1) ? X + 2 : X + 1;
-        for (int yy = ya; yy <= yb; ++yy)
-            for (int xx = xa; xx <= xb; ++xx)
-                *reinterpret_cast<uint4*>(dst + (((static_cast<size_t>(b) * Hop + yy) * Wop + xx) * C + c8 * 8) * 2) = o;
-    }
-}
-int launch_upsample2x(const void* src, void* dst, int B, int H, int W, int Hp, int Wp, int Hop, int Wop, int C, bool bf16,
-                      cudaStream_t st) {
-    if (C % 8) return set_error("upsample2x: C=%d must be a multiple of 8", C);
-    const size_t total = static_cast<size_t>(B) * 4 * H * W * (C / 8);
-    const int threads = 256;
-    const int blocks = static_cast<int>(std::min<size_t>((total + threads - 1) / threads, 148 * 32));
-    if (bf16) upsample2x_kernel<true><<<blocks, threads, 0, st>>>(static_cast<const uint8_t*>(src), static_cast<uint8_t*>(dst), B, H, W, Hp, Wp, Hop, Wop, C);
-    else upsample2x_kernel<false><<<blocks, threads, 0, st>>>(static_cast<const uint8_t*>(src), static_cast<uint8_t*>(dst), B, H, W, Hp, Wp, Hop, Wop, C);
     CUDA_TRY(cudaGetLastError());
     return 0;
 }

@@ -60,11 +60,6 @@ int launch_layernorm(const float* x, const float* gamma, const float* beta, void
 // scale head: metric_scale[b] = exp(MLP(cls[b]))
 int launch_scale_head(const float* cls, const float* const* w, const float* const* bias, const int* dims, int nlayers,
                       int B, float* out, float* scratch, cudaStream_t st);
-// bilinear x2 (align_corners=False) NHWC padded -> NHWC padded (+ replicated border)
-int launch_upsample2x(const void* src, void* dst, int B, int H, int W, int Hp, int Wp, int Hop, int Wop, int C, bool bf16,
-                      cudaStream_t st);
-// zero / replicate helpers
-int launch_fill_border(void* buf, int B, int H, int W, int Hp, int Wp, int C, cudaStream_t st);
 // K17: bilinear resize of the low-res head maps to (H,W) + remap -> points (B,H,W,3), normal (B,H,W,3), mask prob (B,H,W)
 int launch_head_output(const float4* pts_lr, const float4* nrm_lr, const float* msk_lr, int B, int Hl, int Wl, int H, int W,
                        int remap_mode, float* points, float* normal, float* mask, cudaStream_t st);

@@ -87,20 +87,8 @@ __device__ __forceinline__ float gelu_erf(float x) {
     return fmaf(-0.5f, t, fmaxf(x, 0.0f));
 }
 
-// 64-byte (32 x 16-bit) store of one pixel's channel chunk into a padded NHWC buffer, replicating into the 1-pixel
-// border when the pixel lies on the image edge (so that 3x3 taps of the consumer never need clamping).
-__device__ __forceinline__ void store_px_border(uint8_t* base, int b, int Y, int X, int Ho, int Wo, int Hop, int Wop,
-                                                int ld, int c0, const uint4* q) {
-    const int y0 = (Y == 0) ? 0 : Y + 1, y1 = (Y == Ho - 1) ? Y + 2 : Y + 1;
-    const int x0 = (X == 0) ? 0 : X + 1, x1 = (X == Wo - 1) ? X + 2 : X + 1;
-    for (int yy = y0; yy <= y1; ++yy)
-        for (int xx = x0; xx <= x1; ++xx) {
-            uint4* dst = reinterpret_cast<uint4*>(base + ((static_cast<size_t>(b) * Hop + yy) * Wop + xx) * ld * 2 + c0 * 2);
-            dst[0] = q[0]; dst[1] = q[1]; dst[2] = q[2]; dst[3] = q[3];
-        }
-}
-
-// same for an 8-byte (4 x 16-bit) piece
+// 8-byte (4 x 16-bit) store of one pixel's channel group into a padded NHWC buffer, replicating into the 1-pixel border
+// when the pixel lies on the image edge (so that 3x3 taps of the consumer never need clamping).  Cold path: edge pixels only.
 static __device__ __noinline__ void store_px_border8(uint8_t* base, int b, int Y, int X, int Ho, int Wo, int Hop, int Wop,
                                                  int ld, int c0, uint2 q) {
     uint8_t* centre = base + (((static_cast<size_t>(b) * Hop + Y + 1) * Wop + X + 1) * ld + c0) * 2;
