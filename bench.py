@@ -263,13 +263,13 @@ def run_engine(a):
 
     total_prof_ms = sum(ms_op)
     idx, t, fl, by = cls(("gemm.",))
-    roofline = {"kernel": "umma_kernel<AMODE_ROWS> (encoder linears: patch/qkv/proj/fc1/fc2/taps)", "bound": "tensor",
+    roofline = {"kernel": "umma2_kernel (cta_group::2) + umma_kernel<AMODE_ROWS>: encoder linears patch/qkv/proj/fc1/fc2/taps", "bound": "tensor",
                 "achieved": fl / t / 1e12, "peak": pk["tflops"], "unit": "TFLOP/s", "frac": fl / t / 1e12 / pk["tflops"],
                 "traffic": None, "launches": len(idx), "ms_per_step": t * 1e3, "share_of_step": t * 1e3 / total_prof_ms,
                 "peak_source": pk["source"]}
-    idx, t, fl, by = cls(("conv", "upsample2x"))
+    idx, t, fl, by = cls(("conv",))
     dec_bound_s = max(fl / (pk["tflops"] * 1e12), by / (pk["hbm_gbs"] * 1e9))
-    roofline_decoder = {"kernel": "umma_kernel<AMODE_TILES> (implicit-GEMM convs) + upsample2x", "bound": "hbm",
+    roofline_decoder = {"kernel": "umma_kernel<AMODE_TILES> + conv64_kernel (implicit-GEMM convs)", "bound": "hbm",
                         "achieved": by / t / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": by / t / 1e9 / pk["hbm_gbs"],
                         "tensor_tflops": fl / t / 1e12, "frac_of_max_bound": dec_bound_s / t, "traffic": None, "launches": len(idx),
                         "ms_per_step": t * 1e3, "share_of_step": t * 1e3 / total_prof_ms}

@@ -111,6 +111,7 @@ struct moge_engine {
     std::vector<std::unique_ptr<Plan>> plans;
     Plan* last_plan = nullptr;
     bool use_graphs = true;
+    bool use_2cta = false;
     cudaStream_t own_stream = nullptr;
     cudaEvent_t ev_in = nullptr, ev_out = nullptr;
 
@@ -498,8 +499,15 @@ static int add_linear(moge_engine* e, Plan* pl, const void* A, int M, int K, int
     p.out0 = out; p.bias = bias; p.vec1 = v1; p.ldo = ldo; p.T = T; p.W = gridw;
     CUtensorMap ma, mb;
     MG_TRY(make_map_2d(&ma, A, K, M, lda, TILE_M));
-    MG_TRY(make_map_2d(&mb, W, K, N, lda, bn));
     const bool bf16 = e->bf16; const int sms = e->num_sms;
+    const double flops2 = 2.0 * M * static_cast<double>(N) * K;
+    if (bn == 256 && e->use_2cta && (epi == EPI_STORE16 || epi == EPI_GELU16 || epi == EPI_RESID)) {
+        MG_TRY(make_map_2d(&mb, W, K, N, lda, 128));
+        double bytes2 = static_cast<double>(M) * K * 2 + static_cast<double>(N) * K * 2 + ((epi == EPI_RESID) ? static_cast<double>(M) * N * 8 : static_cast<double>(M) * N * 2);
+        pl->ops.add([=](cudaStream_t st) { return launch_umma2(epi, bf16, ma, mb, p, sms, st); }, name, flops2, bytes2);
+        return 0;
+    }
+    MG_TRY(make_map_2d(&mb, W, K, N, lda, bn));
     const double flops = 2.0 * M * static_cast<double>(N) * K;
     double bytes = static_cast<double>(M) * K * 2 + static_cast<double>(N) * K * 2;
     bytes += (epi == EPI_RESID) ? static_cast<double>(M) * N * 8 : (epi == EPI_PATCH) ? static_cast<double>(M) * N * 4 + static_cast<double>(T) * N * 4
@@ -775,6 +783,8 @@ int moge_engine_create(const moge_config_t* cfg, int device, moge_engine_t** out
     e->cfg = *cfg; e->device = device; e->num_sms = prop.multiProcessorCount; e->bf16 = cfg->compute_dtype == MOGE_BF16;
     const char* env = getenv("MOGE_B200_GRAPHS");
     e->use_graphs = !(env && env[0] == '0');
+    const char* env2 = getenv("MOGE_B200_2CTA");
+    e->use_2cta = !(env2 != nullptr && env2[0] == '0');
     if (cudaStreamCreateWithFlags(&e->own_stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreateWithFlags(&e->ev_in, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&e->ev_out, cudaEventDisableTiming) != cudaSuccess) {
@@ -944,6 +954,11 @@ int moge_postprocess(float* points, const float* normal_in, const float* mask_pr
 }
 
 // ---------------------------------------------------------------------------------- operator-level entry points
+static bool use_2cta() {
+    const char* v = getenv("MOGE_B200_2CTA");      // default on; MOGE_B200_2CTA=0 falls back to the 1-CTA kernel
+    return !(v != nullptr && v[0] == '0');
+}
+
 static int dev_sms() {
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
@@ -963,6 +978,10 @@ int moge_op_linear(const void* x, const void* w, const float* bias, const float*
     p.out0 = out; p.bias = bias; p.vec1 = gamma; p.ldo = N;
     CUtensorMap ma, mb;
     MG_TRY(make_map_2d(&ma, x, K, M, K, TILE_M));
+    if (bn == 256 && use_2cta()) {
+        MG_TRY(make_map_2d(&mb, w, K, N, K, 128));
+        return launch_umma2(epi, dtype == MOGE_BF16, ma, mb, p, dev_sms(), static_cast<cudaStream_t>(stream));
+    }
     MG_TRY(make_map_2d(&mb, w, K, N, K, bn));
     return launch_umma(bn, AMODE_ROWS, epi, dtype == MOGE_BF16, ma, ma, mb, p, dev_sms(), static_cast<cudaStream_t>(stream));
 }

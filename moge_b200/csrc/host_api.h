@@ -34,6 +34,8 @@ struct UmmaParams;
 int launch_umma(int bn, int amode, int epi, bool bf16, const CUtensorMap& a, const CUtensorMap& aux, const CUtensorMap& b,
                 const UmmaParams& p, int num_sms, cudaStream_t st);
 
+// 2-CTA (cta_group::2) encoder GEMM, 256x256 pair tiles; a, b: box {64,128}
+int launch_umma2(int epi, bool bf16, const CUtensorMap& a, const CUtensorMap& b, const UmmaParams& p, int num_sms, cudaStream_t st);
 // 3x3 conv with C_in = 64: resident weights + 3 halo boxes per tile (conv64_kernel.cuh); a: box {64,16,10}, aux: box {64,16,8}
 int launch_conv64(int bn, int epi, bool bf16, const CUtensorMap& a, const CUtensorMap& aux, const CUtensorMap& w, const UmmaParams& p,
                   int num_sms, cudaStream_t st);
