@@ -309,7 +309,7 @@ __device__ __forceinline__ void epilogue_tile(const UmmaParams& p, int mt, int n
     }
 }
 
-template <int BN, int AMODE, int EPI, bool BF16>
+template <int BN, int AMODE, int EPI, bool BF16, int DF = -1>
 __global__ void __launch_bounds__(UmmaCfg<BN>::kThreads, 1)
 umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapAux,
             const __grid_constant__ CUtensorMap mapB, const UmmaParams p) {
@@ -423,7 +423,7 @@ umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
             tc_fence_after();
             const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN + col_begin;
 
-            epilogue_tile<BN, Cfg::kColsPerWarp, AMODE, EPI, BF16>(p, mt, nt, t_addr, scr, quarter, lane, col_begin);
+            epilogue_tile<BN, Cfg::kColsPerWarp, AMODE, EPI, BF16, DF>(p, mt, nt, t_addr, scr, quarter, lane, col_begin);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tempty[acc]);

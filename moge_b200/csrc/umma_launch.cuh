@@ -5,11 +5,11 @@
 
 namespace mg {
 
-template <int BN, int AMODE, int EPI, bool BF16>
+template <int BN, int AMODE, int EPI, bool BF16, int DF = -1>
 int launch_umma_inst(const CUtensorMap& a, const CUtensorMap& aux, const CUtensorMap& b, const UmmaParams& p, int num_sms,
                      cudaStream_t st) {
     using Cfg = UmmaCfg<BN>;
-    auto kern = umma_kernel<BN, AMODE, EPI, BF16>;
+    auto kern = umma_kernel<BN, AMODE, EPI, BF16, DF>;
     static bool attr_set = false;
     if (!attr_set) {
         CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));

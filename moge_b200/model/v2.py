@@ -67,6 +67,7 @@ class MoGeModel:
         self._workspace: Optional[torch.Tensor] = None
         self._warned_fp32 = False
         self.training = False
+        self.max_chunk_tokens = 48 * 1370          # images per engine call = max_chunk_tokens // (tokens per image)
 
     # ------------------------------------------------------------------ nn.Module-like plumbing
     @property
@@ -242,18 +243,28 @@ class MoGeModel:
             image = image.float()
         image = image.contiguous()
         dev = self._device
+        # images are independent: large batches run as chunks of at most `max_chunk_tokens` tokens so that the activation
+        # workspace stays bounded (ViT-L, 1370 tokens/image: 32 images ~ 21 GB)
+        chunk = max(1, min(B, self.max_chunk_tokens // (h * w + 1)))
         with torch.cuda.device(dev):
-            ws = self._get_workspace(B, H, W, h, w)
+            ws = self._get_workspace(chunk, H, W, h, w)
             base = ws.data_ptr()
             aligned = (base + 1023) & ~1023
             points = torch.empty(B, H, W, 3, dtype=torch.float32, device=dev) if hasattr(self, "points_head") else None
             normal = torch.empty(B, H, W, 3, dtype=torch.float32, device=dev) if hasattr(self, "normal_head") else None
             mask = torch.empty(B, H, W, dtype=torch.float32, device=dev) if hasattr(self, "mask_head") else None
             scale = torch.empty(B, dtype=torch.float32, device=dev) if hasattr(self, "scale_head") else None
-            capi.check(capi.lib().moge_engine_forward(
-                self._engine, image.data_ptr(), capi.torch_dtype_code(image.dtype), B, H, W, h, w, aligned,
-                ws.numel() - (aligned - base), capi.ptr(points), capi.ptr(normal), capi.ptr(mask), capi.ptr(scale),
-                capi.current_stream()))
+            for lo in range(0, B, chunk):
+                n = min(chunk, B - lo)
+                sub = lambda t: None if t is None else t[lo:lo + n]
+                if n != chunk:          # ragged tail: its own plan / workspace size
+                    ws = self._get_workspace(n, H, W, h, w)
+                    base = ws.data_ptr()
+                    aligned = (base + 1023) & ~1023
+                capi.check(capi.lib().moge_engine_forward(
+                    self._engine, image[lo:lo + n].data_ptr(), capi.torch_dtype_code(image.dtype), n, H, W, h, w, aligned,
+                    ws.numel() - (aligned - base), capi.ptr(sub(points)), capi.ptr(sub(normal)), capi.ptr(sub(mask)),
+                    capi.ptr(sub(scale)), capi.current_stream()))
         return points, normal, mask, scale
 
     def engine_ops(self):

@@ -192,6 +192,21 @@ def test_batch_invariance_and_squeeze():
     assert rel_l2(one["intrinsics"], full["intrinsics"][1]) < 1e-5
 
 
+def test_batch_chunking_is_transparent():
+    model, cfg, sd = get_model("vits", True, 1)
+    img = synthetic_images(5, 70, 98, 31).to(DEV)
+    full = model.forward(img, 100)
+    old = model.max_chunk_tokens
+    try:
+        model.max_chunk_tokens = 2 * 101 + 5          # 2 images per engine call -> chunks of 2, 2, 1
+        chunked = model.forward(img, 100)
+    finally:
+        model.max_chunk_tokens = old
+    torch.cuda.synchronize()
+    for k in full:
+        assert torch.equal(full[k], chunked[k]), k
+
+
 def test_known_fov_branch_matches_port():
     model, cfg, sd = get_model("vits", True, 1)
     img = synthetic_images(2, 84, 112, 22)
