@@ -169,10 +169,16 @@ attention_kernel(const __grid_constant__ CUtensorMap mapQKV, const AttnParams p)
 #pragma unroll
                 for (int i = 0; i < ATT_BKV; ++i) v[i] = (i < kv_left) ? v[i] : -INFINITY;
             }
-            float mx = fmax3(v[0], v[1], v[2]);
+            // four independent max chains (a single serial chain of 64 dependent FMNMX3 costs ~300 cycles per tile with only
+            // two softmax warps per scheduler to hide it)
+            float mx0 = fmax3(v[0], v[1], v[2]), mx1 = fmax3(v[3], v[4], v[5]), mx2 = fmax3(v[6], v[7], v[8]), mx3 = fmax3(v[9], v[10], v[11]);
 #pragma unroll
-            for (int i = 3; i + 1 < ATT_BKV; i += 2) mx = fmax3(mx, v[i], v[i + 1]);
-            mx = fmaxf(mx, v[ATT_BKV - 1]);
+            for (int i = 12; i + 7 < ATT_BKV; i += 8) {
+                mx0 = fmax3(mx0, v[i], v[i + 1]); mx1 = fmax3(mx1, v[i + 2], v[i + 3]);
+                mx2 = fmax3(mx2, v[i + 4], v[i + 5]); mx3 = fmax3(mx3, v[i + 6], v[i + 7]);
+            }
+            mx0 = fmax3(mx0, v[ATT_BKV - 4], v[ATT_BKV - 3]); mx1 = fmax3(mx1, v[ATT_BKV - 2], v[ATT_BKV - 1]);
+            const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
             const float m_new = fmaxf(m, mx);
             const bool grow = (m_new - m) * sc > 8.0f;        // true on the first tile (m = -inf)
             if (j > 0) {
@@ -196,16 +202,19 @@ attention_kernel(const __grid_constant__ CUtensorMap mapQKV, const AttnParams p)
             }
             if (grow) m = m_new;
             const float mb = m * sc;
-            float lsum = 0.f;
+            float ls0 = 0.f, ls1 = 0.f, ls2 = 0.f, ls3 = 0.f;     // independent partial sums (no serial FADD chain)
 #pragma unroll
             for (int c = 0; c < ATT_BKV; c += 32) {
                 uint32_t w[16];
 #pragma unroll
-                for (int i = 0; i < 32; i += 2) {
-                    const float p0 = ex2_approx(fmaf(v[c + i], sc, -mb));
-                    const float p1 = ex2_approx(fmaf(v[c + i + 1], sc, -mb));
-                    lsum += p0 + p1;
-                    w[i >> 1] = H::pack(p0, p1);
+                for (int i = 0; i < 32; i += 8) {
+                    const float p0 = ex2_approx(fmaf(v[c + i], sc, -mb)), p1 = ex2_approx(fmaf(v[c + i + 1], sc, -mb));
+                    const float p2 = ex2_approx(fmaf(v[c + i + 2], sc, -mb)), p3 = ex2_approx(fmaf(v[c + i + 3], sc, -mb));
+                    const float p4 = ex2_approx(fmaf(v[c + i + 4], sc, -mb)), p5 = ex2_approx(fmaf(v[c + i + 5], sc, -mb));
+                    const float p6 = ex2_approx(fmaf(v[c + i + 6], sc, -mb)), p7 = ex2_approx(fmaf(v[c + i + 7], sc, -mb));
+                    ls0 += p0 + p1; ls1 += p2 + p3; ls2 += p4 + p5; ls3 += p6 + p7;
+                    w[(i >> 1)] = H::pack(p0, p1); w[(i >> 1) + 1] = H::pack(p2, p3);
+                    w[(i >> 1) + 2] = H::pack(p4, p5); w[(i >> 1) + 3] = H::pack(p6, p7);
                 }
                 uint8_t* atom = myP + (c >> 6) * ATT_TILE_BYTES;
                 const int chunk0 = (c & 63) >> 3;            // 16-byte chunk index of column c within the 128-byte row
@@ -214,7 +223,7 @@ attention_kernel(const __grid_constant__ CUtensorMap mapQKV, const AttnParams p)
                     *reinterpret_cast<uint4*>(atom + (((chunk0 + q) ^ sw) << 4)) =
                         make_uint4(w[4 * q], w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]);
             }
-            l += lsum;
+            l += (ls0 + ls1) + (ls2 + ls3);
             fence_proxy_async_smem();
             tc_fence_before();
             __syncwarp();
