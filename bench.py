@@ -53,7 +53,7 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks + throttle reasons sampled every 200 ms while the timed region runs."""
+    """nvidia-smi clocks + throttle reasons sampled (~every 50-100 ms) while the timed region runs."""
 
     def __init__(self, index):
         self.index, self.rows, self.stop_flag, self.th = index, [], threading.Event(), None
@@ -69,7 +69,7 @@ class ClockSampler:
                     self.rows.append([c.strip() for c in out.split(",")])
             except Exception:
                 pass
-            self.stop_flag.wait(0.2)
+            self.stop_flag.wait(0.05)
 
     def start(self):
         self.th = threading.Thread(target=self._run, daemon=True)
