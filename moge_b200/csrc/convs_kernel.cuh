@@ -1,14 +1,13 @@
 // "Swapped" implicit-GEMM 3x3 convolution for 64-channel maps (decoder levels 3 and 4).
 //
-// Measured on B200: one tcgen05.mma with M=128 costs ~128 cycles whatever N is, so the pixel-major formulation
-// (M = 128 pixels, N = C_out = 64) runs the tensor pipe at 25 % and N = 16 (folded head outputs) at 6 %.  Here the
-// operands are swapped: the WEIGHTS are the M-side operand (M = 64 output channels, resident in shared memory) and a
-// 16x16-pixel window is the N-side operand (N = 256), D^T[co, pixel] accumulating in TMEM.  One instruction now covers
-// 256 pixels instead of 128, and the three vertical taps of a halo box are 2 KB-aligned row windows of the same box.
+// Idea: make the WEIGHTS the M-side operand (M = 64 output channels, resident in shared memory) and a 16x16-pixel window
+// the N-side operand (N = 256), D^T[co, pixel] accumulating in TMEM, so that one instruction covers 256 pixels; the three
+// vertical taps of a halo box are 2 KB-aligned row windows of the same box.
 //
 // STATUS (round 1): correct (tests/test_gpu_ops.py::test_conv3x3_swapped_operands) but measured ~15 % SLOWER end to end than
-// conv64_kernel on the level-3 convs (its scalar smem transpose and half-idle store lanes cost more than the better MMA
-// shape gains), so the engine only routes to it when MOGE_B200_CONVS=1.  Kept as the starting point for round 2.
+// conv64_kernel on the level-3 convs: tools/mma_cost.cu shows an M=64 tcgen05.mma costs exactly as much as an M=128 one
+// (N/2 cycles, 48-cycle floor), so the swap halves the tensor throughput per instruction, and the scalar smem transpose plus
+// half-idle store lanes add epilogue cost.  The engine only routes to it when MOGE_B200_CONVS=1.
 //
 // TMEM layout of an M=64 accumulator (cta_group::1): row r sits in lane (r%16) + 32*(r/16), i.e. each warp quarter owns
 // 16 output channels in its lower 16 lanes.  The epilogue transposes 32-pixel chunks through shared memory so that
