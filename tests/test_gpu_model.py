@@ -232,3 +232,45 @@ def test_from_pretrained_roundtrip(tmp_path):
     torch.cuda.synchronize()
     assert set(out.keys()) == {"points", "intrinsics", "depth", "mask", "normal"}
     assert out["points"].shape == (70, 98, 3)
+
+
+def test_c_abi_error_paths():
+    """Error behaviour through the C ABI: negative return code + message, no crash, engine stays usable."""
+    import ctypes as C
+    from moge_b200 import capi
+    L = capi.lib()
+    model, cfg, sd = get_model("vits", True, 1)
+    img = synthetic_images(1, 70, 98, 3).to(DEV)
+    model.forward(img, 100)                                   # makes sure the engine exists
+    n = C.c_size_t()
+    assert L.moge_engine_workspace_bytes(model._engine, 0, 70, 98, 7, 10, C.byref(n)) != 0
+    assert b"bad shape" in L.moge_last_error()
+    pts = torch.empty(1, 70, 98, 3, device=DEV)
+    ws = torch.empty(1 << 20, dtype=torch.uint8, device=DEV)
+    base = (ws.data_ptr() + 1023) & ~1023
+    rc = L.moge_engine_forward(model._engine, img.data_ptr(), capi.F32, 1, 70, 98, 7, 10, base, 1 << 19, pts.data_ptr(), None, None, None,
+                               capi.current_stream())
+    assert rc != 0 and b"workspace too small" in L.moge_last_error()
+    rc = L.moge_engine_forward(model._engine, img.data_ptr(), capi.F32, 1, 70, 98, 7, 10, base + 8, 1 << 19, pts.data_ptr(), None, None, None,
+                               capi.current_stream())
+    assert rc != 0 and b"aligned" in L.moge_last_error()
+    assert L.moge_engine_set_weight(model._engine, b"x", img.data_ptr(), (C.c_int64 * 1)(3), 1, capi.F32, None) != 0   # finalized
+    h = C.c_void_p()
+    c = capi.make_config(cfg, capi.F16)
+    c.num_heads = 5
+    assert L.moge_engine_create(C.byref(c), 0, C.byref(h)) != 0 and b"head_dim" in L.moge_last_error()
+    out = model.forward(img, 100)                             # still healthy
+    torch.cuda.synchronize()
+    assert torch.isfinite(out["points"]).all()
+
+
+def test_missing_weight_is_reported():
+    from moge_b200 import capi
+    cfg = model_config("vits", True)
+    sd = make_state_dict(cfg, 0)
+    sd.pop("neck.res_blocks.2.1.layers.5.weight")
+    m = MoGeModel(**cfg)
+    m.load_state_dict(sd)
+    m = m.to(DEV)
+    with pytest.raises(capi.MogeError, match="missing weight 'neck.res_blocks.2.1.layers.5.weight'"):
+        m.forward(synthetic_images(1, 70, 98, 3).to(DEV), 100)

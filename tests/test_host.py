@@ -56,3 +56,48 @@ def test_import_model_class_by_version():
     assert import_model_class_by_version("v2") is MoGeModel
     with pytest.raises(NotImplementedError):
         import_model_class_by_version("v1")
+
+
+def test_make_config_rejects_unsupported_decoders():
+    cfg = model_config("vits")
+    bad = {**cfg, "neck": {**cfg["neck"], "res_block_in_norm": "layer_norm"}}
+    with pytest.raises(capi.MogeError):
+        capi.make_config(bad, capi.F16)
+    bad = {**cfg, "points_head": {**cfg["points_head"], "resamplers": ["pixel_shuffle"] * 4}}
+    with pytest.raises(capi.MogeError):
+        capi.make_config(bad, capi.F16)
+    with pytest.raises(ValueError):
+        capi.make_config({**cfg, "encoder": {**cfg["encoder"], "backbone": "dinov2_vitg14"}}, capi.F16)
+
+
+def test_model_plumbing_without_gpu():
+    """nn.Module-like surface of the drop-in class (v2.py:59-74,109-120): dtype/device bookkeeping, training-only stubs."""
+    from moge.model.v2 import MoGeModel
+    m = MoGeModel(**model_config("vits", with_normal=False), some_deprecated_kwarg=1) if False else MoGeModel(**model_config("vits", with_normal=False))
+    assert not hasattr(m, "normal_head") and hasattr(m, "points_head") and hasattr(m, "scale_head")
+    assert m.dtype == torch.float32 and m.half().dtype == torch.float16 and m.bfloat16().dtype == torch.bfloat16
+    assert m.eval() is m and m.device.type == "cpu"
+    with pytest.raises(NotImplementedError):
+        m.init_weights()
+    with pytest.raises(NotImplementedError):
+        m.enable_gradient_checkpointing()
+    with pytest.raises(NotImplementedError):
+        m.onnx_compatible_mode = True
+    assert m.onnx_compatible_mode is False
+    with pytest.warns(UserWarning):
+        MoGeModel(**model_config("vits"), deprecated_thing=3)          # v2.py:42-43
+
+
+def test_synthetic_checkpoint_roundtrip(tmp_path):
+    """The synthetic checkpoint is a reference-format file: {'model_config', 'model'} loadable with weights_only=True."""
+    from moge.model.v2 import MoGeModel
+    from moge_b200.synthetic import save_checkpoint, make_state_dict
+    cfg = model_config("vits")
+    path = tmp_path / "model.pt"
+    save_checkpoint(path, cfg, seed=3)
+    ck = torch.load(path, map_location="cpu", weights_only=True)
+    assert set(ck) == {"model_config", "model"}
+    m = MoGeModel.from_pretrained(path)
+    sd = make_state_dict(cfg, 3)
+    assert set(m.state_dict()) == set(sd) and all(torch.equal(m.state_dict()[k], sd[k]) for k in sd)
+    assert m.num_tokens_range == [1200, 3600] and m.remap_output == "exp"
