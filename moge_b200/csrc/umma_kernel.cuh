@@ -102,13 +102,150 @@ static __device__ __noinline__ void store_px_border8(uint8_t* base, int b, int Y
             if (dy != 0 || dx != 0) *reinterpret_cast<uint2*>(centre + dy * rowp + dx * colp) = q;
 }
 
+// DF < 0: the EPI_DEC variant (raw / ReLU copies, skip, UV, pixel shuffle) is decided at run time from the params;
+// DF >= 0: compile-time bit mask (DF_RAW | DF_RELU | DF_SKIP | DF_UV | DF_SHUFFLE) -- a much smaller hot loop.
+enum : int { DF_RAW = 1, DF_RELU = 2, DF_SKIP = 4, DF_UV = 8, DF_SHUFFLE = 16 };
+
+// 16-byte flavour of the border-replicating store (8 x 16-bit channels of one pixel).  Cold path: edge pixels only.
+static __device__ __noinline__ void store_px_border16(uint8_t* base, int b, int Y, int X, int Ho, int Wo, int Hop, int Wop,
+                                                      int ld, int c0, uint4 q) {
+    uint8_t* centre = base + (((static_cast<size_t>(b) * Hop + Y + 1) * Wop + X + 1) * ld + c0) * 2;
+    const int dy0 = (Y == 0) ? -1 : 0, dy1 = (Y == Ho - 1) ? 1 : 0;
+    const int dx0 = (X == 0) ? -1 : 0, dx1 = (X == Wo - 1) ? 1 : 0;
+    const ptrdiff_t rowp = static_cast<ptrdiff_t>(Wop) * ld * 2, colp = static_cast<ptrdiff_t>(ld) * 2;
+    for (int dy = dy0; dy <= dy1; ++dy)
+        for (int dx = dx0; dx <= dx1; ++dx)
+            if (dy != 0 || dx != 0) *reinterpret_cast<uint4*>(centre + dy * rowp + dx * colp) = q;
+}
+
+// EPI_DEC epilogue (decoder maps, padded NHWC): after the 32x32 transpose every lane owns EIGHT channels of one pixel
+// (4 lanes per pixel row, 8 pixels per warp instruction, 4 passes per chunk) and moves 16 bytes per load/store -- half the
+// per-byte instruction overhead of the 8-byte variant used for the row-major epilogues.
+template <int BN, int COLS, int AMODE, bool BF16, int DF>
+__device__ __forceinline__ void epilogue_dec16(const UmmaParams& p, int mt, int nt, uint32_t t_addr, float4* scr, int quarter, int lane,
+                                               int col_begin) {
+    using H = H16<BF16>;
+    const bool has_raw = (DF < 0) ? (p.out0 != nullptr) : ((DF & DF_RAW) != 0);
+    const bool has_relu = (DF < 0) ? (p.out1 != nullptr) : ((DF & DF_RELU) != 0);
+    const bool has_skip = (DF < 0) ? (p.skip != nullptr) : ((DF & DF_SKIP) != 0);
+    const bool has_uv = (DF < 0) ? (p.vec1 != nullptr) : ((DF & DF_UV) != 0);
+    const bool shuffle = (DF < 0) ? (p.shuffle != 0) : ((DF & DF_SHUFFLE) != 0);
+    const int sub = lane >> 2;        // which of the 8 rows of a pass this lane serves
+    const int q8 = lane & 3;          // which group of 8 channels of the 32-column chunk
+    int tile_b = 0, tile_y0 = 0, tile_x0 = 0;
+    if (AMODE == AMODE_TILES) {
+        const int per_img = p.tiles_x * p.tiles_y;
+        tile_b = mt / per_img;
+        const int r = mt % per_img;
+        tile_y0 = (r / p.tiles_x) * TILE_PH;
+        tile_x0 = (r % p.tiles_x) * TILE_PW;
+    }
+    bool ok[4];
+    int rb[4], ry[4], rx[4], eflags[4];
+    size_t roff[4];                   // byte offset of the centre output pixel (channel 0)
+    const int sh = shuffle ? 2 : 1;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int rl = quarter * 32 + 8 * i + sub;
+        if (AMODE == AMODE_ROWS) {
+            const long grow = static_cast<long>(mt) * TILE_M + rl;
+            ok[i] = grow < p.M;
+            rb[i] = static_cast<int>(grow / p.T);
+            const int t = static_cast<int>(grow % p.T);
+            ry[i] = t / p.W; rx[i] = t % p.W;
+        } else {
+            rb[i] = tile_b;
+            ry[i] = tile_y0 + rl / TILE_PW;
+            rx[i] = tile_x0 + rl % TILE_PW;
+            ok[i] = (ry[i] < p.H) && (rx[i] < p.W);
+        }
+        roff[i] = ((static_cast<size_t>(rb[i]) * p.Hop + sh * ry[i] + 1) * p.Wop + sh * rx[i] + 1) * p.ldo * 2;
+        eflags[i] = (ry[i] == 0 ? 1 : 0) | (ry[i] == p.H - 1 ? 2 : 0) | (rx[i] == 0 ? 4 : 0) | (rx[i] == p.W - 1 ? 8 : 0);
+    }
+    const float inv_wo = 1.0f / static_cast<float>(p.Wo), inv_ho = 1.0f / static_cast<float>(p.Ho);
+#pragma unroll 1
+    for (int c = 0; c < COLS; c += 32) {
+        float v[32];
+        tmem_ld32(t_addr + c, v);
+        tc_wait_ld();
+#pragma unroll
+        for (int q = 0; q < 8; ++q) scr[lane * 8 + (q ^ (lane & 7))] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+        __syncwarp();
+        const int col = nt * BN + col_begin + c;
+        int co = col + 8 * q8, qd = 0, qmask = 15;
+        size_t qoff = 0;
+        if (shuffle) {
+            qd = col / p.ldo;                              // ldo == C_out; a 32-column chunk never straddles a phase
+            co -= qd * p.ldo;
+            qoff = (static_cast<size_t>(qd >> 1) * p.Wop + (qd & 1)) * p.ldo * 2;
+            qmask = ((qd >> 1) ? 2 : 1) | ((qd & 1) ? 8 : 4);
+        }
+        qoff += static_cast<size_t>(co) * 2;
+        const float4 b0 = *reinterpret_cast<const float4*>(p.bias + co), b1 = *reinterpret_cast<const float4*>(p.bias + co + 4);
+        float4 g0 = make_float4(0.f, 0.f, 0.f, 0.f), g1 = g0, h0 = g0, h1 = g0;
+        if (has_uv) {
+            g0 = *reinterpret_cast<const float4*>(p.vec1 + co); g1 = *reinterpret_cast<const float4*>(p.vec1 + co + 4);
+            h0 = *reinterpret_cast<const float4*>(p.vec2 + co); h1 = *reinterpret_cast<const float4*>(p.vec2 + co + 4);
+        }
+        // phase 1: all global reads of the chunk back to back
+        uint4 sk[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            sk[i] = make_uint4(0u, 0u, 0u, 0u);
+            if (has_skip && ok[i]) sk[i] = *reinterpret_cast<const uint4*>(static_cast<const uint8_t*>(p.skip) + roff[i] + qoff);
+        }
+        // phase 2: math + 16-byte stores
+        uint4 pk_raw[4], pk_relu[4];
+        unsigned edge_rows = 0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int rl = 8 * i + sub;
+            float4 a0 = scr[rl * 8 + ((2 * q8) ^ (rl & 7))];
+            float4 a1 = scr[rl * 8 + ((2 * q8 + 1) ^ (rl & 7))];
+            if (!ok[i]) continue;
+            a0.x += b0.x; a0.y += b0.y; a0.z += b0.z; a0.w += b0.w;
+            a1.x += b1.x; a1.y += b1.y; a1.z += b1.z; a1.w += b1.w;
+            if (has_skip) {
+                const float2 s0 = H::unpack(sk[i].x), s1 = H::unpack(sk[i].y), s2 = H::unpack(sk[i].z), s3 = H::unpack(sk[i].w);
+                a0.x += s0.x; a0.y += s0.y; a0.z += s1.x; a0.w += s1.y;
+                a1.x += s2.x; a1.y += s2.y; a1.z += s3.x; a1.w += s3.y;
+            }
+            if (has_uv) {
+                const int X = sh * rx[i] + (qd & 1), Y = sh * ry[i] + (qd >> 1);
+                const float uu = p.su * ((2 * X + 1) * inv_wo - 1.0f);
+                const float vv = p.sv * ((2 * Y + 1) * inv_ho - 1.0f);
+                a0.x += g0.x * uu + h0.x * vv; a0.y += g0.y * uu + h0.y * vv; a0.z += g0.z * uu + h0.z * vv; a0.w += g0.w * uu + h0.w * vv;
+                a1.x += g1.x * uu + h1.x * vv; a1.y += g1.y * uu + h1.y * vv; a1.z += g1.z * uu + h1.z * vv; a1.w += g1.w * uu + h1.w * vv;
+            }
+            if ((eflags[i] & qmask) != 0) edge_rows |= 1u << i;
+            if (has_raw) {
+                pk_raw[i] = make_uint4(H::pack(a0.x, a0.y), H::pack(a0.z, a0.w), H::pack(a1.x, a1.y), H::pack(a1.z, a1.w));
+                *reinterpret_cast<uint4*>(static_cast<uint8_t*>(p.out0) + roff[i] + qoff) = pk_raw[i];
+            }
+            if (has_relu) {
+                pk_relu[i] = make_uint4(H::pack(fmaxf(a0.x, 0.f), fmaxf(a0.y, 0.f)), H::pack(fmaxf(a0.z, 0.f), fmaxf(a0.w, 0.f)),
+                                        H::pack(fmaxf(a1.x, 0.f), fmaxf(a1.y, 0.f)), H::pack(fmaxf(a1.z, 0.f), fmaxf(a1.w, 0.f)));
+                *reinterpret_cast<uint4*>(static_cast<uint8_t*>(p.out1) + roff[i] + qoff) = pk_relu[i];
+            }
+        }
+        if (edge_rows != 0) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+                if (edge_rows >> i & 1) {
+                    const int X = sh * rx[i] + (qd & 1), Y = sh * ry[i] + (qd >> 1);
+                    if (has_raw) store_px_border16(static_cast<uint8_t*>(p.out0), rb[i], Y, X, p.Ho, p.Wo, p.Hop, p.Wop, p.ldo, co, pk_raw[i]);
+                    if (has_relu) store_px_border16(static_cast<uint8_t*>(p.out1), rb[i], Y, X, p.Ho, p.Wo, p.Hop, p.Wop, p.ldo, co, pk_relu[i]);
+                }
+        }
+        __syncwarp();
+    }
+}
+
+
 // Epilogue of ONE accumulator tile for one epilogue warp (TMEM lane quarter `quarter`, columns [col_begin, col_begin+COLS)).
 // TMEM hands each thread one accumulator ROW; global memory wants warps on contiguous COLUMNS.  Every 32x32 chunk is
 // therefore transposed through a per-warp swizzled smem tile: afterwards 8 lanes x float4 cover the 32 columns of one
 // row and each warp instruction touches 4 rows (4 x 128 B), fully coalesced.
-// DF < 0: the EPI_DEC variant (raw / ReLU copies, skip, UV, pixel shuffle) is decided at run time from the params;
-// DF >= 0: compile-time bit mask (DF_RAW | DF_RELU | DF_SKIP | DF_UV | DF_SHUFFLE) -- a much smaller hot loop.
-enum : int { DF_RAW = 1, DF_RELU = 2, DF_SKIP = 4, DF_UV = 8, DF_SHUFFLE = 16 };
 
 template <int BN, int COLS, int AMODE, int EPI, bool BF16, int DF = -1>
 __device__ __forceinline__ void epilogue_tile(const UmmaParams& p, int mt, int nt, uint32_t t_addr, float4* scr, int quarter,
@@ -119,6 +256,10 @@ __device__ __forceinline__ void epilogue_tile(const UmmaParams& p, int mt, int n
     const bool has_skip = (DF < 0) ? (p.skip != nullptr) : ((DF & DF_SKIP) != 0);
     const bool has_uv = (DF < 0) ? (p.vec1 != nullptr) : ((DF & DF_UV) != 0);
     const bool shuffle = (DF < 0) ? (p.shuffle != 0) : ((DF & DF_SHUFFLE) != 0);
+    if (EPI == EPI_DEC) {
+        epilogue_dec16<BN, COLS, AMODE, BF16, DF>(p, mt, nt, t_addr, scr, quarter, lane, col_begin);
+        return;
+    }
     const int row = quarter * 32 + lane;
     const int sub = lane >> 3;        // which of the 4 rows of a pass this lane serves
     const int q4 = lane & 7;          // which float4 (4 columns) of the 32-column chunk
