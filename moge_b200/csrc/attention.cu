@@ -2,7 +2,10 @@
 // scale hd^-0.5, no mask) as one tcgen05 kernel: S = Q K^T and O~ = P V on the tensor cores with TMEM accumulators,
 // single-pass online softmax in registers (the whole 128-wide score row lives in registers; FMNMX3 + MUFU.EX2),
 // O accumulated in TMEM by the MMA itself and rescaled lazily (only when the running max grows by more than 2^8),
-// two 128-row query tiles per CTA ping-ponging on the tensor pipe.
+// two 128-row query tiles per CTA ping-ponging on the tensor pipe.  The probabilities P never touch shared memory: the
+// softmax threads store them (16-bit, packed) into tensor memory and the P V MMA reads its A operand from there -- with
+// P in smem the kernel was shared-memory-bandwidth-bound (P write + P read were half of all smem traffic and the MMAs
+// ran at 2.3x their nominal duration waiting for operands).
 //
 // Layout: qkv is the QKV-GEMM output [B, N, 3*D] (16-bit); Q/K/V tiles of head h are the column windows
 // [h*64, D+h*64, 2D+h*64) fetched by TMA straight from that buffer (no head-major repack): Q and K tiles are
@@ -16,11 +19,11 @@ namespace mg {
 constexpr int ATT_HD = 64;
 constexpr int ATT_BQ = 128;       // query rows per softmax warpgroup
 constexpr int ATT_BKV = 128;      // keys per tile
-constexpr int ATT_KV_STAGES = 3;
+constexpr int ATT_KV_STAGES = 5;
 constexpr int ATT_TILE_BYTES = 128 * 128;   // [128 rows][64 x 16-bit]
 constexpr int ATT_THREADS = 128 + 256;   // warpgroup 0: TMA warp, MMA warp, 2 idle; warpgroups 1,2: softmax
-// smem: Q0,Q1 | K[3] | V[3] | P0 (2 atoms) | P1 (2 atoms) | barriers
-constexpr int ATT_SMEM = (2 + 2 * ATT_KV_STAGES + 4) * ATT_TILE_BYTES + 1024 + 256;
+// smem: Q0,Q1 | K[stages] | V[stages] | barriers
+constexpr int ATT_SMEM = (2 + 2 * ATT_KV_STAGES) * ATT_TILE_BYTES + 1024 + 256;
 
 struct AttnParams {
     void* out;        // [B*N, D] 16-bit
@@ -34,25 +37,26 @@ attention_kernel(const __grid_constant__ CUtensorMap mapQKV, const AttnParams p)
     using H = H16<BF16>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    constexpr int ST = ATT_KV_STAGES;
     uint8_t* sQ = smem;                                        // 2 tiles
-    uint8_t* sK = sQ + 2 * ATT_TILE_BYTES;                     // 3 tiles
-    uint8_t* sV = sK + ATT_KV_STAGES * ATT_TILE_BYTES;         // 3 tiles
-    uint8_t* sP = sV + ATT_KV_STAGES * ATT_TILE_BYTES;         // 2 groups x 2 atoms
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 4 * ATT_TILE_BYTES);
+    uint8_t* sK = sQ + 2 * ATT_TILE_BYTES;
+    uint8_t* sV = sK + ST * ATT_TILE_BYTES;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sV + ST * ATT_TILE_BYTES);
     uint64_t* q_full = bars;                 // 1
-    uint64_t* k_full = bars + 1;             // 3
-    uint64_t* k_empty = bars + 4;            // 3
-    uint64_t* v_full = bars + 7;             // 3
-    uint64_t* v_empty = bars + 10;           // 3
-    uint64_t* s_full = bars + 13;            // 2
-    uint64_t* p_full = bars + 15;            // 2
-    uint64_t* o_full = bars + 17;            // 2 (one per group; completes once per kv tile)
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 19);
+    uint64_t* k_full = bars + 1;
+    uint64_t* k_empty = k_full + ST;
+    uint64_t* v_full = k_empty + ST;
+    uint64_t* v_empty = v_full + ST;
+    uint64_t* s_full = v_empty + ST;         // 2
+    uint64_t* p_full = s_full + 2;           // 2
+    uint64_t* o_full = p_full + 2;           // 2 (one per group; completes once per kv tile)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int q0 = blockIdx.x * 2 * ATT_BQ;
     const int h = blockIdx.y, b = blockIdx.z;
     const int nkv = (p.N + ATT_BKV - 1) / ATT_BKV;
+    const int ng = (q0 + ATT_BQ < p.N) ? 2 : 1;       // the second query tile of the last CTA may be entirely past N: skipped
 
     if (threadIdx.x == 0) {
         tma_prefetch_desc(&mapQKV);
@@ -72,7 +76,7 @@ attention_kernel(const __grid_constant__ CUtensorMap mapQKV, const AttnParams p)
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
-    // TMEM columns: S0 [0,128)  S1 [128,256)  O0 [256,320)  O1 [320,384)
+    // TMEM columns: S0 [0,128)  S1 [128,256)  O0 [256,320)  O1 [320,384)  P0 [384,448)  P1 [448,512)  (P: 2 x 16-bit per column)
 
     // register re-balancing between the control warpgroup and the two softmax warpgroups (row of 128 scores in registers)
     if (warp == 0) {
@@ -105,16 +109,15 @@ attention_kernel(const __grid_constant__ CUtensorMap mapQKV, const AttnParams p)
                 umma_commit(&s_full[g]);
             };
             auto issue_pv = [&](int g, int j) {
-                const uint32_t pa = smem_u32(sP + g * 2 * ATT_TILE_BYTES);
+                const uint32_t pa = tmem + 384 + g * 64;
                 const uint32_t va = smem_u32(sV + (j % ATT_KV_STAGES) * ATT_TILE_BYTES);
                 const uint32_t d = tmem + 256 + g * 64;
 #pragma unroll
                 for (int k = 0; k < ATT_BKV / 16; ++k) {
-                    // A: P, K-major; 4 K-steps per 64-column swizzle atom (atoms 16 KB apart)
-                    const uint64_t a = make_sdesc_sw128(pa + (k >> 2) * ATT_TILE_BYTES) + 2 * (k & 3);
+                    // A: P in tensor memory, 16 keys (= 8 columns of packed 16-bit pairs) per K-step
                     // B: V tile [kv][hd]: MN-major, 16 kv rows (= 2 groups of 8 x 128 B) per K-step
                     const uint64_t bd = make_sdesc_sw128(va + k * 16 * 128, /*lbo=*/ATT_TILE_BYTES, /*sbo=*/1024);
-                    umma_f16(d, a, bd, idesc_o, (j | k) != 0);       // O accumulates across kv tiles in TMEM
+                    umma_f16_ts(d, pa + 8 * k, bd, idesc_o, (j | k) != 0);       // O accumulates across kv tiles in TMEM
                 }
                 umma_commit(&o_full[g]);
             };
@@ -122,21 +125,21 @@ attention_kernel(const __grid_constant__ CUtensorMap mapQKV, const AttnParams p)
             mbar_wait(&k_full[0], 0);
             tc_fence_after();
             issue_s(0, 0);
-            issue_s(1, 0);
+            if (ng == 2) issue_s(1, 0);
             umma_commit(&k_empty[0]);
             for (int j = 0; j < nkv; ++j) {
-                for (int g = 0; g < 2; ++g) {
+                for (int g = 0; g < ng; ++g) {
                     mbar_wait(&p_full[g], j & 1);
                     tc_fence_after();
                     if (j + 1 < nkv) {
                         const int s1 = (j + 1) % ATT_KV_STAGES;
                         if (g == 0) { mbar_wait(&k_full[s1], ((j + 1) / ATT_KV_STAGES) & 1); tc_fence_after(); }
                         issue_s(g, j + 1);
-                        if (g == 1) umma_commit(&k_empty[s1]);
+                        if (g == ng - 1) umma_commit(&k_empty[s1]);
                     }
                     if (g == 0) { mbar_wait(&v_full[j % ATT_KV_STAGES], (j / ATT_KV_STAGES) & 1); tc_fence_after(); }
                     issue_pv(g, j);
-                    if (g == 1) umma_commit(&v_empty[j % ATT_KV_STAGES]);
+                    if (g == ng - 1) umma_commit(&v_empty[j % ATT_KV_STAGES]);
                 }
             }
         }
@@ -152,12 +155,11 @@ attention_kernel(const __grid_constant__ CUtensorMap mapQKV, const AttnParams p)
         const uint32_t lane_sel = static_cast<uint32_t>(quarter * 32) << 16;
         const uint32_t tS = tmem + lane_sel + g * 128;
         const uint32_t tO = tmem + lane_sel + 256 + g * 64;
-        uint8_t* myP = sP + g * 2 * ATT_TILE_BYTES + (row >> 3) * 1024 + (row & 7) * 128;
-        const int sw = row & 7;
+        const uint32_t tP = tmem + lane_sel + 384 + g * 64;
         float m = -INFINITY;            // reference max of the exponent (may lag the true running max by < 2^8)
         float l = 0.f;
         const float sc = p.scale_log2;
-        for (int j = 0; j < nkv; ++j) {
+        for (int j = 0; j < (g < ng ? nkv : 0); ++j) {
             mbar_wait(&s_full[g], j & 1);
             tc_fence_after();
             float v[ATT_BKV];
@@ -216,19 +218,15 @@ attention_kernel(const __grid_constant__ CUtensorMap mapQKV, const AttnParams p)
                     w[(i >> 1)] = H::pack(p0, p1); w[(i >> 1) + 1] = H::pack(p2, p3);
                     w[(i >> 1) + 2] = H::pack(p4, p5); w[(i >> 1) + 3] = H::pack(p6, p7);
                 }
-                uint8_t* atom = myP + (c >> 6) * ATT_TILE_BYTES;
-                const int chunk0 = (c & 63) >> 3;            // 16-byte chunk index of column c within the 128-byte row
-#pragma unroll
-                for (int q = 0; q < 4; ++q)
-                    *reinterpret_cast<uint4*>(atom + (((chunk0 + q) ^ sw) << 4)) =
-                        make_uint4(w[4 * q], w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]);
+                tmem_st16(tP + (c >> 1), w);
             }
             l += (ls0 + ls1) + (ls2 + ls3);
-            fence_proxy_async_smem();
+            tc_wait_st();
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&p_full[g]);
         }
+        if (g < ng) {
         mbar_wait(&o_full[g], (nkv - 1) & 1);
         tc_fence_after();
         const float inv = 1.0f / l;
@@ -247,6 +245,7 @@ attention_kernel(const __grid_constant__ CUtensorMap mapQKV, const AttnParams p)
                 dst[0] = q[0]; dst[1] = q[1]; dst[2] = q[2]; dst[3] = q[3];
             }
             __syncwarp();
+        }
         }
     }
     tc_fence_before();

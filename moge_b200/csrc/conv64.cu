@@ -47,3 +47,12 @@ int launch_conv64(int bn, int epi, bool bf16, const CUtensorMap& a, const CUtens
 }
 
 }  // namespace mg
+
+#ifdef MG_C64_DEBUG
+extern "C" int mg_debug_c64(unsigned long long* out, int reset) {
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(out, mg::mg_c64_dbg, sizeof(unsigned long long) * 8);
+    if (reset) { unsigned long long z[8] = {0}; cudaMemcpyToSymbol(mg::mg_c64_dbg, z, sizeof(z)); }
+    return 0;
+}
+#endif

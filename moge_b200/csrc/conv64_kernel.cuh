@@ -11,16 +11,31 @@
 
 namespace mg {
 
+#ifdef MG_C64_DEBUG
+// wait-time attribution (debug builds only): [0] producer waits for a free stage, [1] MMA waits for data, [2] MMA waits for
+// a free accumulator, [3] epilogue warp 2 waits for an accumulator, [4] epilogue warp 2 busy, [5] CTA lifetime, [6] tiles
+__device__ unsigned long long mg_c64_dbg[8];
+#define C64_T0() const long long _t0 = clock64()
+#define C64_ACC(var) var += clock64() - _t0
+#else
+#define C64_T0()
+#define C64_ACC(var)
+#endif
+
 template <int BN> struct Conv64Cfg {
     static constexpr int kABytes = 160 * 128;                       // box {64 ch, 16 px, 10 rows}
     static constexpr int kWBytes = BN * 128 * 10;                   // 9 taps + 1 aux block, each [BN][64] 128B-swizzled
-    static constexpr int kStages = (BN >= 64) ? 5 : 6;
-    // 4 TMEM accumulator stages; the 8 epilogue warps form TWO groups of 4 (one warp per TMEM lane quarter) that drain
-    // alternate tiles concurrently, so the per-tile epilogue latency chain (TMEM load -> transpose -> global) overlaps.
-    static constexpr int kAccStages = 4;
-    static constexpr int kEpiWarps = 8;
+#ifndef MG_C64_GROUPS
+#define MG_C64_GROUPS 2
+#endif
+    static constexpr int kEpiGroups = MG_C64_GROUPS;
+    static constexpr int kStages = (BN >= 64) ? (kEpiGroups > 2 ? 4 : 5) : 6;
+    // 2 TMEM accumulator stages per epilogue group; the epilogue warps form kEpiGroups groups of 4 (one warp per TMEM lane quarter) that drain
+    // tiles round-robin, concurrently, so the per-tile epilogue latency chain (TMEM load -> transpose -> global) overlaps.
+    static constexpr int kAccStages = 2 * kEpiGroups;
+    static constexpr int kEpiWarps = 4 * kEpiGroups;
     static constexpr int kThreads = 64 + 32 * kEpiWarps;
-    static constexpr int kTmemCols = (kAccStages * BN <= 32) ? 32 : (kAccStages * BN <= 64) ? 64 : (kAccStages * BN <= 128) ? 128 : 256;
+    static constexpr int kTmemCols = (kAccStages * BN <= 32) ? 32 : (kAccStages * BN <= 64) ? 64 : (kAccStages * BN <= 128) ? 128 : (kAccStages * BN <= 256) ? 256 : 512;
     static constexpr int kScratchBytes = kEpiWarps * 4096;
     static constexpr int kSmemBytes = kStages * kABytes + kWBytes + 1024 + 256 + kScratchBytes;
     static constexpr int kColsPerWarp = BN;
@@ -44,6 +59,10 @@ conv64_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
     float* scratch_base = reinterpret_cast<float*>(sW + Cfg::kWBytes + 256);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#ifdef MG_C64_DEBUG
+    long long dbg_a = 0, dbg_b = 0;
+    const long long dbg_start = clock64();
+#endif
     const int nnt = p.num_n_tiles;
     const int nt = blockIdx.x % nnt;                  // this CTA's output-channel tile (weights stay resident)
     const int mt0 = blockIdx.x / nnt, mstep = gridDim.x / nnt;
@@ -75,7 +94,7 @@ conv64_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
                 const int b = mt / per_img, r = mt % per_img;
                 const int y0 = (r / p.tiles_x) * TILE_PH, x0 = (r % p.tiles_x) * TILE_PW;
                 for (int i = 0; i < nstage; ++i) {
-                    mbar_wait(&empty[s], ph ^ 1);
+                    { C64_T0(); mbar_wait(&empty[s], ph ^ 1); C64_ACC(dbg_a); }
                     uint8_t* sa = smem + s * Cfg::kABytes;
                     if (i < 3) {
                         mbar_arrive_expect_tx(&full[s], Cfg::kABytes);
@@ -97,11 +116,11 @@ conv64_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
             const uint32_t w0 = smem_u32(sW);
             for (int mt = mt0; mt < p.num_m_tiles; mt += mstep, ++it) {
                 const int acc = it % Cfg::kAccStages;
-                mbar_wait(&tempty[acc], ((it / Cfg::kAccStages) & 1) ^ 1);
+                { C64_T0(); mbar_wait(&tempty[acc], ((it / Cfg::kAccStages) & 1) ^ 1); C64_ACC(dbg_b); }
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * BN;
                 for (int i = 0; i < nstage; ++i) {
-                    mbar_wait(&full[s], ph);
+                    { C64_T0(); mbar_wait(&full[s], ph); C64_ACC(dbg_a); }
                     tc_fence_after();
                     const uint32_t sa = smem_u32(smem + s * Cfg::kABytes);
                     if (i < 3) {
@@ -127,20 +146,29 @@ conv64_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
     } else {
         const int ew = warp - 2;
         const int quarter = warp & 3;
-        const int group = ew >> 2;                     // epilogue group 0 drains even tiles, group 1 odd tiles
+        const int group = ew >> 2;                     // epilogue group g drains tiles g, g + G, ...
         float4* scr = reinterpret_cast<float4*>(scratch_base + ew * 1024);
         int it = group;
-        for (int mt = mt0 + group * mstep; mt < p.num_m_tiles; mt += 2 * mstep, it += 2) {
+        for (int mt = mt0 + group * mstep; mt < p.num_m_tiles; mt += Cfg::kEpiGroups * mstep, it += Cfg::kEpiGroups) {
             const int acc = it % Cfg::kAccStages;
-            mbar_wait(&tfull[acc], (it / Cfg::kAccStages) & 1);
+            { C64_T0(); mbar_wait(&tfull[acc], (it / Cfg::kAccStages) & 1); C64_ACC(dbg_a); }
             tc_fence_after();
             const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN;
+            { C64_T0();
             epilogue_tile<BN, Cfg::kColsPerWarp, AMODE_TILES, EPI, BF16, DF>(p, mt, nt, t_addr, scr, quarter, lane, 0);
+            C64_ACC(dbg_b); }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tempty[acc]);
         }
     }
+#ifdef MG_C64_DEBUG
+    if (lane == 0) {
+        if (warp == 0) { atomicAdd(&mg_c64_dbg[0], (unsigned long long)dbg_a); atomicAdd(&mg_c64_dbg[5], (unsigned long long)(clock64() - dbg_start)); }
+        if (warp == 1) { atomicAdd(&mg_c64_dbg[1], (unsigned long long)dbg_a); atomicAdd(&mg_c64_dbg[2], (unsigned long long)dbg_b); }
+        if (warp == 2) { atomicAdd(&mg_c64_dbg[3], (unsigned long long)dbg_a); atomicAdd(&mg_c64_dbg[4], (unsigned long long)dbg_b); }
+    }
+#endif
     tc_fence_before();
     __syncthreads();
     if (warp == 1) {
