@@ -25,6 +25,18 @@ constexpr int ATT_THREADS = 128 + 256;   // warpgroup 0: TMA warp, MMA warp, 2 i
 // smem: Q0,Q1 | K[stages] | V[stages] | barriers
 constexpr int ATT_SMEM = (2 + 2 * ATT_KV_STAGES) * ATT_TILE_BYTES + 1024 + 256;
 
+#ifdef MG_ATT_DEBUG
+// wait-time attribution (debug builds only; tools/att_debug.py), summed over CTAs, warp 4 lane 0 / warp 1 lane 0:
+// [0] softmax waits S  [1] softmax waits PV(j-1)  [2] softmax loop total  [3] MMA waits P  [4] MMA waits K/V
+// [5] CTA lifetime  [6] prologue (start -> first S)  [7] epilogue (O normalise + store)
+__device__ unsigned long long mg_att_dbg[8];
+#define ATT_T0() const long long _t0 = clock64()
+#define ATT_ACC(var) var += clock64() - _t0
+#else
+#define ATT_T0()
+#define ATT_ACC(var)
+#endif
+
 struct AttnParams {
     void* out;        // [B*N, D] 16-bit
     int B, N, D, heads;
@@ -53,6 +65,10 @@ attention_kernel(const __grid_constant__ CUtensorMap mapQKV, const AttnParams p)
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#ifdef MG_ATT_DEBUG
+    long long dbg_a = 0, dbg_b = 0, dbg_c = 0, dbg_d = 0;
+    const long long dbg_start = clock64();
+#endif
     const int q0 = blockIdx.x * 2 * ATT_BQ;
     const int h = blockIdx.y, b = blockIdx.z;
     const int nkv = (p.N + ATT_BKV - 1) / ATT_BKV;
@@ -81,66 +97,85 @@ attention_kernel(const __grid_constant__ CUtensorMap mapQKV, const AttnParams p)
     // register re-balancing between the control warpgroup and the two softmax warpgroups (row of 128 scores in registers)
     if (warp == 0) {
         asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
-        if (lane == 0) {
+        // The warp stays converged and ONE ELECTED lane issues (here and in the MMA warp): under `if (lane == 0)` the
+        // compiler wraps every TMA / tcgen05 instruction in an elect-and-retry loop, ~9 dependent instructions per MMA.
+        if (elect_one()) {
             mbar_arrive_expect_tx(q_full, 2 * ATT_TILE_BYTES);
             tma_load_3d(sQ, &mapQKV, q_full, h * ATT_HD, q0, b);
             tma_load_3d(sQ + ATT_TILE_BYTES, &mapQKV, q_full, h * ATT_HD, q0 + ATT_BQ, b);
-            for (int j = 0; j < nkv; ++j) {
-                const int s = j % ATT_KV_STAGES;
-                const uint32_t ph = (j / ATT_KV_STAGES) & 1;
-                mbar_wait(&k_empty[s], ph ^ 1);
+        }
+        __syncwarp();
+        int s = 0; uint32_t ph = 0;
+        for (int j = 0; j < nkv; ++j) {
+            mbar_wait(&k_empty[s], ph ^ 1);
+            if (elect_one()) {
                 mbar_arrive_expect_tx(&k_full[s], ATT_TILE_BYTES);
                 tma_load_3d(sK + s * ATT_TILE_BYTES, &mapQKV, &k_full[s], p.D + h * ATT_HD, j * ATT_BKV, b);
-                mbar_wait(&v_empty[s], ph ^ 1);
+            }
+            __syncwarp();
+            mbar_wait(&v_empty[s], ph ^ 1);
+            if (elect_one()) {
                 mbar_arrive_expect_tx(&v_full[s], ATT_TILE_BYTES);
                 tma_load_3d(sV + s * ATT_TILE_BYTES, &mapQKV, &v_full[s], 2 * p.D + h * ATT_HD, j * ATT_BKV, b);
             }
+            __syncwarp();
+            if (++s == ATT_KV_STAGES) { s = 0; ph ^= 1; }
         }
     } else if (warp == 1) {
         asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
-        if (lane == 0) {
+        {
             constexpr uint32_t idesc_s = make_idesc(128, ATT_BKV, BF16 ? 1u : 0u, 0, 0);   // Q (K-major) x K (K-major)
-            constexpr uint32_t idesc_o = make_idesc(128, ATT_HD, BF16 ? 1u : 0u, 0, 1);    // P (K-major) x V (MN-major)
-            auto issue_s = [&](int g, int j) {
-                const uint64_t a = make_sdesc_sw128(smem_u32(sQ + g * ATT_TILE_BYTES));
-                const uint64_t bd = make_sdesc_sw128(smem_u32(sK + (j % ATT_KV_STAGES) * ATT_TILE_BYTES));
+            constexpr uint32_t idesc_o = make_idesc(128, ATT_HD, BF16 ? 1u : 0u, 0, 1);    // P (TMEM) x V (MN-major)
+            // S_g = Q_g K_stage^T; `release` != 0: the K stage is free once these MMAs retire
+            auto issue_s = [&](int g, int stage, bool release) {
+                if (elect_one()) {
+                    const uint64_t a = make_sdesc_sw128(smem_u32(sQ + g * ATT_TILE_BYTES));
+                    const uint64_t bd = make_sdesc_sw128(smem_u32(sK + stage * ATT_TILE_BYTES));
 #pragma unroll
-                for (int k = 0; k < ATT_HD / 16; ++k) umma_f16(tmem + g * 128, a + 2 * k, bd + 2 * k, idesc_s, k != 0);
-                umma_commit(&s_full[g]);
-            };
-            auto issue_pv = [&](int g, int j) {
-                const uint32_t pa = tmem + 384 + g * 64;
-                const uint32_t va = smem_u32(sV + (j % ATT_KV_STAGES) * ATT_TILE_BYTES);
-                const uint32_t d = tmem + 256 + g * 64;
-#pragma unroll
-                for (int k = 0; k < ATT_BKV / 16; ++k) {
-                    // A: P in tensor memory, 16 keys (= 8 columns of packed 16-bit pairs) per K-step
-                    // B: V tile [kv][hd]: MN-major, 16 kv rows (= 2 groups of 8 x 128 B) per K-step
-                    const uint64_t bd = make_sdesc_sw128(va + k * 16 * 128, /*lbo=*/ATT_TILE_BYTES, /*sbo=*/1024);
-                    umma_f16_ts(d, pa + 8 * k, bd, idesc_o, (j | k) != 0);       // O accumulates across kv tiles in TMEM
+                    for (int k = 0; k < ATT_HD / 16; ++k) umma_f16(tmem + g * 128, a + 2 * k, bd + 2 * k, idesc_s, k != 0);
+                    umma_commit(&s_full[g]);
+                    if (release) umma_commit(&k_empty[stage]);
                 }
-                umma_commit(&o_full[g]);
+                __syncwarp();
+            };
+            // O_g (+)= P_g V_stage
+            auto issue_pv = [&](int g, int stage, bool first, bool release) {
+                if (elect_one()) {
+                    const uint32_t pa = tmem + 384 + g * 64;
+                    const uint32_t va = smem_u32(sV + stage * ATT_TILE_BYTES);
+                    const uint32_t d = tmem + 256 + g * 64;
+#pragma unroll
+                    for (int k = 0; k < ATT_BKV / 16; ++k) {
+                        // A: P in tensor memory, 16 keys (= 8 columns of packed 16-bit pairs) per K-step
+                        // B: V tile [kv][hd]: MN-major, 16 kv rows (= 2 groups of 8 x 128 B) per K-step
+                        const uint64_t bd = make_sdesc_sw128(va + k * 16 * 128, /*lbo=*/ATT_TILE_BYTES, /*sbo=*/1024);
+                        umma_f16_ts(d, pa + 8 * k, bd, idesc_o, !(first && k == 0));   // O accumulates across kv tiles in TMEM
+                    }
+                    umma_commit(&o_full[g]);
+                    if (release) umma_commit(&v_empty[stage]);
+                }
+                __syncwarp();
             };
             mbar_wait(q_full, 0);
             mbar_wait(&k_full[0], 0);
             tc_fence_after();
-            issue_s(0, 0);
-            if (ng == 2) issue_s(1, 0);
-            umma_commit(&k_empty[0]);
+            issue_s(0, 0, ng == 1);
+            if (ng == 2) issue_s(1, 0, true);
+            int sv = 0; uint32_t phv = 0;         // V stage of tile j
+            int sk = 1 % ATT_KV_STAGES; uint32_t phk = (ATT_KV_STAGES == 1) ? 1u : 0u;   // K stage of tile j + 1
             for (int j = 0; j < nkv; ++j) {
                 for (int g = 0; g < ng; ++g) {
-                    mbar_wait(&p_full[g], j & 1);
+                    { ATT_T0(); mbar_wait(&p_full[g], j & 1); ATT_ACC(dbg_a); }
                     tc_fence_after();
                     if (j + 1 < nkv) {
-                        const int s1 = (j + 1) % ATT_KV_STAGES;
-                        if (g == 0) { mbar_wait(&k_full[s1], ((j + 1) / ATT_KV_STAGES) & 1); tc_fence_after(); }
-                        issue_s(g, j + 1);
-                        if (g == ng - 1) umma_commit(&k_empty[s1]);
+                        if (g == 0) { ATT_T0(); mbar_wait(&k_full[sk], phk); tc_fence_after(); ATT_ACC(dbg_b); }
+                        issue_s(g, sk, g == ng - 1);
                     }
-                    if (g == 0) { mbar_wait(&v_full[j % ATT_KV_STAGES], (j / ATT_KV_STAGES) & 1); tc_fence_after(); }
-                    issue_pv(g, j);
-                    if (g == ng - 1) umma_commit(&v_empty[j % ATT_KV_STAGES]);
+                    if (g == 0) { ATT_T0(); mbar_wait(&v_full[sv], phv); tc_fence_after(); ATT_ACC(dbg_b); }
+                    issue_pv(g, sv, j == 0, g == ng - 1);
                 }
+                if (++sv == ATT_KV_STAGES) { sv = 0; phv ^= 1; }
+                if (++sk == ATT_KV_STAGES) { sk = 0; phk ^= 1; }
             }
         }
     } else if (warp < 4) {
@@ -159,8 +194,14 @@ attention_kernel(const __grid_constant__ CUtensorMap mapQKV, const AttnParams p)
         float m = -INFINITY;            // reference max of the exponent (may lag the true running max by < 2^8)
         float l = 0.f;
         const float sc = p.scale_log2;
+#ifdef MG_ATT_DEBUG
+        const long long dbg_loop0 = clock64();
+#endif
         for (int j = 0; j < (g < ng ? nkv : 0); ++j) {
-            mbar_wait(&s_full[g], j & 1);
+            { ATT_T0(); mbar_wait(&s_full[g], j & 1); ATT_ACC(dbg_a); }
+#ifdef MG_ATT_DEBUG
+            if (j == 0) dbg_d = dbg_a;
+#endif
             tc_fence_after();
             float v[ATT_BKV];
 #pragma unroll
@@ -185,7 +226,7 @@ attention_kernel(const __grid_constant__ CUtensorMap mapQKV, const AttnParams p)
             const bool grow = (m_new - m) * sc > 8.0f;        // true on the first tile (m = -inf)
             if (j > 0) {
                 // PV(j-1) must have finished before P is overwritten (and before O is touched)
-                mbar_wait(&o_full[g], (j - 1) & 1);
+                { ATT_T0(); mbar_wait(&o_full[g], (j - 1) & 1); ATT_ACC(dbg_b); }
                 tc_fence_after();
                 if (__any_sync(0xffffffffu, grow)) {
                     const float alpha = grow ? ex2_approx((m - m_new) * sc) : 1.0f;
@@ -226,6 +267,9 @@ attention_kernel(const __grid_constant__ CUtensorMap mapQKV, const AttnParams p)
             __syncwarp();
             if (lane == 0) mbar_arrive(&p_full[g]);
         }
+#ifdef MG_ATT_DEBUG
+        dbg_c = clock64() - dbg_loop0;
+#endif
         if (g < ng) {
         mbar_wait(&o_full[g], (nkv - 1) & 1);
         tc_fence_after();
@@ -247,7 +291,19 @@ attention_kernel(const __grid_constant__ CUtensorMap mapQKV, const AttnParams p)
             __syncwarp();
         }
         }
+#ifdef MG_ATT_DEBUG
+        if (warp == 4 && lane == 0) {
+            const long long now = clock64();
+            atomicAdd(&mg_att_dbg[0], (unsigned long long)dbg_a); atomicAdd(&mg_att_dbg[1], (unsigned long long)dbg_b);
+            atomicAdd(&mg_att_dbg[2], (unsigned long long)dbg_c); atomicAdd(&mg_att_dbg[5], (unsigned long long)(now - dbg_start));
+            atomicAdd(&mg_att_dbg[6], (unsigned long long)(dbg_loop0 - dbg_start + dbg_d));
+            atomicAdd(&mg_att_dbg[7], (unsigned long long)(now - dbg_loop0 - dbg_c));
+        }
+#endif
     }
+#ifdef MG_ATT_DEBUG
+    if (warp == 1 && lane == 0) { atomicAdd(&mg_att_dbg[3], (unsigned long long)dbg_a); atomicAdd(&mg_att_dbg[4], (unsigned long long)dbg_b); }
+#endif
     tc_fence_before();
     __syncthreads();
     if (warp == 1) {
@@ -275,3 +331,12 @@ int launch_attention(const CUtensorMap& mapQKV, void* out, int B, int N, int D, 
 }
 
 }  // namespace mg
+
+#ifdef MG_ATT_DEBUG
+extern "C" int mg_debug_att(unsigned long long* out, int reset) {
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(out, mg::mg_att_dbg, sizeof(unsigned long long) * 8);
+    if (reset) { unsigned long long z[8] = {0}; cudaMemcpyToSymbol(mg::mg_att_dbg, z, sizeof(z)); }
+    return 0;
+}
+#endif

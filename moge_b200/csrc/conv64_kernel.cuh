@@ -84,10 +84,16 @@ conv64_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
-        if (lane == 0) {
+        // The whole warp walks the loop (converged) and ONE ELECTED lane issues: inside `if (lane == 0)` the compiler must
+        // assume an arbitrary active mask and wraps every TMA / tcgen05 instruction in an elect-and-retry loop (~9
+        // dependent instructions per MMA -- more than a 48-cycle N = 64 MMA takes to execute).
+        {
             const int nblk = 9 + p.kb_aux;
-            mbar_arrive_expect_tx(wfull, nblk * BN * 128);
-            for (int t = 0; t < nblk; ++t) tma_load_2d(sW + t * BN * 128, &mapW, wfull, t * TILE_K, nt * BN);
+            if (elect_one()) {
+                mbar_arrive_expect_tx(wfull, nblk * BN * 128);
+                for (int t = 0; t < nblk; ++t) tma_load_2d(sW + t * BN * 128, &mapW, wfull, t * TILE_K, nt * BN);
+            }
+            __syncwarp();
             int s = 0; uint32_t ph = 0;
             const int per_img = p.tiles_x * p.tiles_y;
             for (int mt = mt0; mt < p.num_m_tiles; mt += mstep) {
@@ -96,19 +102,22 @@ conv64_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
                 for (int i = 0; i < nstage; ++i) {
                     { C64_T0(); mbar_wait(&empty[s], ph ^ 1); C64_ACC(dbg_a); }
                     uint8_t* sa = smem + s * Cfg::kABytes;
-                    if (i < 3) {
-                        mbar_arrive_expect_tx(&full[s], Cfg::kABytes);
-                        tma_load_4d(sa, &mapA, &full[s], 0, x0 + i, y0, b);          // padded rows y0..y0+9 = taps dy 0..2
-                    } else {
-                        mbar_arrive_expect_tx(&full[s], TILE_M * 128);
-                        tma_load_4d(sa, &mapAux, &full[s], 0, x0 + 1, y0 + 1, b);
+                    if (elect_one()) {
+                        if (i < 3) {
+                            mbar_arrive_expect_tx(&full[s], Cfg::kABytes);
+                            tma_load_4d(sa, &mapA, &full[s], 0, x0 + i, y0, b);          // padded rows y0..y0+9 = taps dy 0..2
+                        } else {
+                            mbar_arrive_expect_tx(&full[s], TILE_M * 128);
+                            tma_load_4d(sa, &mapAux, &full[s], 0, x0 + 1, y0 + 1, b);
+                        }
                     }
+                    __syncwarp();
                     if (++s == S) { s = 0; ph ^= 1; }
                 }
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
+        {
             constexpr uint32_t idesc = make_idesc(TILE_M, BN, BF16 ? 1u : 0u);
             mbar_wait(wfull, 0);
             int s = 0; uint32_t ph = 0;
@@ -123,24 +132,27 @@ conv64_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
                     { C64_T0(); mbar_wait(&full[s], ph); C64_ACC(dbg_a); }
                     tc_fence_after();
                     const uint32_t sa = smem_u32(smem + s * Cfg::kABytes);
-                    if (i < 3) {
+                    if (elect_one()) {
+                        if (i < 3) {
 #pragma unroll
-                        for (int dy = 0; dy < 3; ++dy) {
-                            const uint64_t adesc = make_sdesc_sw128(sa + dy * TILE_PW * 128);
-                            const uint64_t bdesc = make_sdesc_sw128(w0 + (dy * 3 + i) * BN * 128);
+                            for (int dy = 0; dy < 3; ++dy) {
+                                const uint64_t adesc = make_sdesc_sw128(sa + dy * TILE_PW * 128);
+                                const uint64_t bdesc = make_sdesc_sw128(w0 + (dy * 3 + i) * BN * 128);
 #pragma unroll
-                            for (int k = 0; k < TILE_K / 16; ++k) umma_f16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (i | dy | k) != 0);
+                                for (int k = 0; k < TILE_K / 16; ++k) umma_f16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (i | dy | k) != 0);
+                            }
+                        } else {
+                            const uint64_t adesc = make_sdesc_sw128(sa);
+                            const uint64_t bdesc = make_sdesc_sw128(w0 + 9 * BN * 128);
+#pragma unroll
+                            for (int k = 0; k < TILE_K / 16; ++k) umma_f16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, 1);
                         }
-                    } else {
-                        const uint64_t adesc = make_sdesc_sw128(sa);
-                        const uint64_t bdesc = make_sdesc_sw128(w0 + 9 * BN * 128);
-#pragma unroll
-                        for (int k = 0; k < TILE_K / 16; ++k) umma_f16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, 1);
+                        umma_commit(&empty[s]);
+                        if (i == nstage - 1) umma_commit(&tfull[acc]);
                     }
-                    umma_commit(&empty[s]);
+                    __syncwarp();
                     if (++s == S) { s = 0; ph ^= 1; }
                 }
-                umma_commit(&tfull[acc]);
             }
         }
     } else {

@@ -102,8 +102,8 @@ umma2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
-        // ================================================================== TMA producer (both CTAs)
-        if (lane == 0) {
+        // ================================================================== TMA producer (both CTAs; converged warp, elected lane issues)
+        {
             int s = 0; uint32_t ph = 0;
             for (int t = pair; t < total; t += npairs) {
                 const int mp = t / p.num_n_tiles, nt = t % p.num_n_tiles;
@@ -114,16 +114,19 @@ umma2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
                     uint8_t* sa = smem + s * Cfg::kStageBytes;
                     uint8_t* sb = sa + TILE_M * 128;
                     const uint32_t lbar = smem_u32(&full[s]) & kPeerMask;
-                    if (leader) mbar_arrive_expect_tx(&full[s], 2 * Cfg::kStageBytes);      // bytes of BOTH CTAs
-                    tma_load_2d_2sm(sa, &mapA, lbar, i * TILE_K, m0);
-                    tma_load_2d_2sm(sb, &mapB, lbar, i * TILE_K, n0);
+                    if (elect_one()) {
+                        if (leader) mbar_arrive_expect_tx(&full[s], 2 * Cfg::kStageBytes);      // bytes of BOTH CTAs
+                        tma_load_2d_2sm(sa, &mapA, lbar, i * TILE_K, m0);
+                        tma_load_2d_2sm(sb, &mapB, lbar, i * TILE_K, n0);
+                    }
+                    __syncwarp();
                     if (++s == S) { s = 0; ph ^= 1; }
                 }
             }
         }
     } else if (warp == 1) {
         // ================================================================== MMA issuer (leader CTA only)
-        if (leader && lane == 0) {
+        if (leader) {
             constexpr uint32_t idesc = make_idesc(256, BN, BF16 ? 1u : 0u);
             int s = 0; uint32_t ph = 0;
             int it = 0;
@@ -138,12 +141,15 @@ umma2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
                     const uint32_t sa = smem_u32(smem + s * Cfg::kStageBytes);
                     const uint64_t adesc = make_sdesc_sw128(sa);
                     const uint64_t bdesc = make_sdesc_sw128(sa + TILE_M * 128);
+                    if (elect_one()) {
 #pragma unroll
-                    for (int k = 0; k < TILE_K / 16; ++k) umma_f16_2sm(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (i | k) != 0);
-                    umma_commit_2sm(&empty[s]);
+                        for (int k = 0; k < TILE_K / 16; ++k) umma_f16_2sm(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (i | k) != 0);
+                        umma_commit_2sm(&empty[s]);
+                        if (i == kb_total - 1) umma_commit_2sm(&tfull[acc]);
+                    }
+                    __syncwarp();
                     if (++s == S) { s = 0; ph ^= 1; }
                 }
-                umma_commit_2sm(&tfull[acc]);
             }
         }
     } else {

@@ -488,7 +488,9 @@ umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
 
     if (warp == 0) {
         // ================================================================== TMA producer
-        if (lane == 0) {
+        // (this warp and the MMA warp stay CONVERGED and one elected lane issues: under `if (lane == 0)` the compiler has
+        // to assume an arbitrary active mask and wraps every TMA / tcgen05 instruction in an elect-and-retry loop)
+        {
             int s = 0; uint32_t ph = 0;
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
                 const int mt = tile / p.num_n_tiles, nt = tile % p.num_n_tiles;
@@ -504,24 +506,27 @@ umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
                     mbar_wait(&empty[s], ph ^ 1);
                     uint8_t* sa = smem + s * Cfg::kStageBytes;
                     uint8_t* sb = sa + TILE_M * 128;
-                    mbar_arrive_expect_tx(&full[s], Cfg::kStageBytes);
-                    if (AMODE == AMODE_ROWS) {
-                        tma_load_2d(sa, &mapA, &full[s], i * TILE_K, mt * TILE_M);
-                    } else if (i < kb_taps) {
-                        const int tap = i / p.kb_main, c = i % p.kb_main;
-                        const int tx = (p.ntaps == 9) ? tap % 3 : 1, ty = (p.ntaps == 9) ? tap / 3 : 1;
-                        tma_load_4d(sa, &mapA, &full[s], c * TILE_K, x0 + tx, y0 + ty, b);
-                    } else {
-                        tma_load_4d(sa, &mapAux, &full[s], (i - kb_taps) * TILE_K, x0 + 1, y0 + 1, b);
+                    if (elect_one()) {
+                        mbar_arrive_expect_tx(&full[s], Cfg::kStageBytes);
+                        if (AMODE == AMODE_ROWS) {
+                            tma_load_2d(sa, &mapA, &full[s], i * TILE_K, mt * TILE_M);
+                        } else if (i < kb_taps) {
+                            const int tap = i / p.kb_main, c = i % p.kb_main;
+                            const int tx = (p.ntaps == 9) ? tap % 3 : 1, ty = (p.ntaps == 9) ? tap / 3 : 1;
+                            tma_load_4d(sa, &mapA, &full[s], c * TILE_K, x0 + tx, y0 + ty, b);
+                        } else {
+                            tma_load_4d(sa, &mapAux, &full[s], (i - kb_taps) * TILE_K, x0 + 1, y0 + 1, b);
+                        }
+                        tma_load_2d(sb, &mapB, &full[s], i * TILE_K, nt * BN);
                     }
-                    tma_load_2d(sb, &mapB, &full[s], i * TILE_K, nt * BN);
+                    __syncwarp();
                     if (++s == S) { s = 0; ph ^= 1; }
                 }
             }
         }
     } else if (warp == 1) {
         // ================================================================== MMA issuer
-        if (lane == 0) {
+        {
             constexpr uint32_t idesc = make_idesc(TILE_M, BN, BF16 ? 1u : 0u);
             int s = 0; uint32_t ph = 0;
             int it = 0;
@@ -537,13 +542,16 @@ umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
                     const uint32_t sa = smem_u32(smem + s * Cfg::kStageBytes);
                     const uint64_t adesc = make_sdesc_sw128(sa);
                     const uint64_t bdesc = make_sdesc_sw128(sa + TILE_M * 128);
+                    if (elect_one()) {
 #pragma unroll
-                    for (int k = 0; k < TILE_K / 16; ++k)
-                        umma_f16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (i | k) != 0);
-                    umma_commit(&empty[s]);
+                        for (int k = 0; k < TILE_K / 16; ++k)
+                            umma_f16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (i | k) != 0);
+                        umma_commit(&empty[s]);
+                        if (i == kb_total - 1) umma_commit(&tfull[acc]);
+                    }
+                    __syncwarp();
                     if (++s == S) { s = 0; ph ^= 1; }
                 }
-                umma_commit(&tfull[acc]);
             }
         }
     } else {
