@@ -62,7 +62,8 @@ attention_kernel(const __grid_constant__ CUtensorMap mapQKV, const AttnParams p)
     uint64_t* s_full = v_empty + ST;         // 2
     uint64_t* p_full = s_full + 2;           // 2
     uint64_t* o_full = p_full + 2;           // 2 (one per group; completes once per kv tile)
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 2);
+    uint64_t* s_free = o_full + 2;           // 2: the softmax threads hold the whole score tile in registers -> S may be overwritten
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_free + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 #ifdef MG_ATT_DEBUG
@@ -83,7 +84,7 @@ attention_kernel(const __grid_constant__ CUtensorMap mapQKV, const AttnParams p)
         }
         for (int g = 0; g < 2; ++g) {
             mbar_init(&s_full[g], 1); mbar_init(&p_full[g], 4);
-            mbar_init(&o_full[g], 1);
+            mbar_init(&o_full[g], 1); mbar_init(&s_free[g], 4);
         }
         fence_mbar_init();
     }
@@ -164,14 +165,20 @@ attention_kernel(const __grid_constant__ CUtensorMap mapQKV, const AttnParams p)
             int sv = 0; uint32_t phv = 0;         // V stage of tile j
             int sk = 1 % ATT_KV_STAGES; uint32_t phk = (ATT_KV_STAGES == 1) ? 1u : 0u;   // K stage of tile j + 1
             for (int j = 0; j < nkv; ++j) {
+                // S(j+1) of both groups first: it only needs the score registers of tile j to be loaded (s_free), not the
+                // softmax of tile j to be finished -- the next scores are ready before the softmax threads ask for them
+                if (j + 1 < nkv) {
+                    { ATT_T0(); mbar_wait(&k_full[sk], phk); ATT_ACC(dbg_b); }
+                    for (int g = 0; g < ng; ++g) {
+                        { ATT_T0(); mbar_wait(&s_free[g], j & 1); ATT_ACC(dbg_a); }
+                        tc_fence_after();
+                        issue_s(g, sk, g == ng - 1);
+                    }
+                }
+                { ATT_T0(); mbar_wait(&v_full[sv], phv); ATT_ACC(dbg_b); }
                 for (int g = 0; g < ng; ++g) {
                     { ATT_T0(); mbar_wait(&p_full[g], j & 1); ATT_ACC(dbg_a); }
                     tc_fence_after();
-                    if (j + 1 < nkv) {
-                        if (g == 0) { ATT_T0(); mbar_wait(&k_full[sk], phk); tc_fence_after(); ATT_ACC(dbg_b); }
-                        issue_s(g, sk, g == ng - 1);
-                    }
-                    if (g == 0) { ATT_T0(); mbar_wait(&v_full[sv], phv); tc_fence_after(); ATT_ACC(dbg_b); }
                     issue_pv(g, sv, j == 0, g == ng - 1);
                 }
                 if (++sv == ATT_KV_STAGES) { sv = 0; phv ^= 1; }
@@ -207,6 +214,9 @@ attention_kernel(const __grid_constant__ CUtensorMap mapQKV, const AttnParams p)
 #pragma unroll
             for (int c = 0; c < ATT_BKV; c += 32) tmem_ld32(tS + c, v + c);
             tc_wait_ld();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&s_free[g]);
             const int kv_left = p.N - j * ATT_BKV;
             if (kv_left < ATT_BKV) {                    // only the last tile has padding columns
 #pragma unroll
@@ -245,23 +255,25 @@ attention_kernel(const __grid_constant__ CUtensorMap mapQKV, const AttnParams p)
             }
             if (grow) m = m_new;
             const float mb = m * sc;
-            float ls0 = 0.f, ls1 = 0.f, ls2 = 0.f, ls3 = 0.f;     // independent partial sums (no serial FADD chain)
+            // exponent argument and row sum with packed 2 x fp32 instructions (FFMA2 / FADD2): the loop is bound by issue slots
+            // and the fma pipe next to the MUFU.EX2 stream, not by the tensor pipe
+            const float2 sc2 = make_float2(sc, sc), nmb2 = make_float2(-mb, -mb);
+            float2 ls01 = make_float2(0.f, 0.f), ls23 = ls01;       // independent partial sums (no serial FADD chain)
 #pragma unroll
             for (int c = 0; c < ATT_BKV; c += 32) {
                 uint32_t w[16];
 #pragma unroll
-                for (int i = 0; i < 32; i += 8) {
-                    const float p0 = ex2_approx(fmaf(v[c + i], sc, -mb)), p1 = ex2_approx(fmaf(v[c + i + 1], sc, -mb));
-                    const float p2 = ex2_approx(fmaf(v[c + i + 2], sc, -mb)), p3 = ex2_approx(fmaf(v[c + i + 3], sc, -mb));
-                    const float p4 = ex2_approx(fmaf(v[c + i + 4], sc, -mb)), p5 = ex2_approx(fmaf(v[c + i + 5], sc, -mb));
-                    const float p6 = ex2_approx(fmaf(v[c + i + 6], sc, -mb)), p7 = ex2_approx(fmaf(v[c + i + 7], sc, -mb));
-                    ls0 += p0 + p1; ls1 += p2 + p3; ls2 += p4 + p5; ls3 += p6 + p7;
-                    w[(i >> 1)] = H::pack(p0, p1); w[(i >> 1) + 1] = H::pack(p2, p3);
-                    w[(i >> 1) + 2] = H::pack(p4, p5); w[(i >> 1) + 3] = H::pack(p6, p7);
+                for (int i = 0; i < 32; i += 4) {
+                    const float2 t0 = ffma2(make_float2(v[c + i], v[c + i + 1]), sc2, nmb2);
+                    const float2 t1 = ffma2(make_float2(v[c + i + 2], v[c + i + 3]), sc2, nmb2);
+                    const float2 e0 = make_float2(ex2_approx(t0.x), ex2_approx(t0.y));
+                    const float2 e1 = make_float2(ex2_approx(t1.x), ex2_approx(t1.y));
+                    ls01 = fadd2(ls01, e0); ls23 = fadd2(ls23, e1);
+                    w[(i >> 1)] = H::pack(e0.x, e0.y); w[(i >> 1) + 1] = H::pack(e1.x, e1.y);
                 }
                 tmem_st16(tP + (c >> 1), w);
             }
-            l += (ls0 + ls1) + (ls2 + ls3);
+            l += (ls01.x + ls01.y) + (ls23.x + ls23.y);
             tc_wait_st();
             tc_fence_before();
             __syncwarp();

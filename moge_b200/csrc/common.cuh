@@ -213,6 +213,27 @@ __device__ __forceinline__ void tmem_st1(uint32_t taddr, float v) {
 }
 __device__ __forceinline__ void tc_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
+// Packed 2 x fp32 arithmetic (Blackwell FFMA2 / FADD2): one issue slot and one fma-pipe pass for two lanes of work.
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
+    unsigned long long ra, rb, rc, rd;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(ra) : "f"(a.x), "f"(a.y));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(rb) : "f"(b.x), "f"(b.y));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(rc) : "f"(c.x), "f"(c.y));
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(ra), "l"(rb), "l"(rc));
+    float2 d;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(d.x), "=f"(d.y) : "l"(rd));
+    return d;
+}
+__device__ __forceinline__ float2 fadd2(float2 a, float2 b) {
+    unsigned long long ra, rb, rd;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(ra) : "f"(a.x), "f"(a.y));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(rb) : "f"(b.x), "f"(b.y));
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(rd) : "l"(ra), "l"(rb));
+    float2 d;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(d.x), "=f"(d.y) : "l"(rd));
+    return d;
+}
+
 __device__ __forceinline__ float fmax3(float a, float b, float c) {
     float r;
     asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
