@@ -87,6 +87,19 @@ __device__ __forceinline__ float gelu_erf(float x) {
     return fmaf(-0.5f, t, fmaxf(x, 0.0f));
 }
 
+// Two lanes of gelu_erf with packed FFMA2/FMUL2 (bit-identical to the scalar version: fma.rn.f32x2 is fmaf per lane).
+__device__ __forceinline__ float2 gelu_erf2(float2 x) {
+    const float2 ab = make_float2(fabsf(x.x), fabsf(x.y));
+    const float2 ax = make_float2(fminf(ab.x, 6.0f), fminf(ab.y, 6.0f));
+    float2 q = ffma2(make_float2(-4.804994387e-04f, -4.804994387e-04f), ax, make_float2(7.133518346e-03f, 7.133518346e-03f));
+    q = ffma2(q, ax, make_float2(-5.194617063e-02f, -5.194617063e-02f));
+    q = ffma2(q, ax, make_float2(-4.598676562e-01f, -4.598676562e-01f));
+    q = ffma2(q, ax, make_float2(-1.150842190e+00f, -1.150842190e+00f));
+    q = ffma2(q, ax, make_float2(-3.041332639e-05f, -3.041332639e-05f));
+    const float2 t = fmul2(ab, make_float2(ex2_approx(q.x), ex2_approx(q.y)));
+    return ffma2(make_float2(-0.5f, -0.5f), t, make_float2(fmaxf(x.x, 0.0f), fmaxf(x.y, 0.0f)));
+}
+
 // 8-byte (4 x 16-bit) store of one pixel's channel group into a padded NHWC buffer, replicating into the 1-pixel border
 // when the pixel lies on the image edge (so that 3x3 taps of the consumer never need clamping).  Cold path: edge pixels only.
 static __device__ __noinline__ void store_px_border8(uint8_t* base, int b, int Y, int X, int Ho, int Wo, int Hop, int Wop,
@@ -405,7 +418,10 @@ __device__ __forceinline__ void epilogue_tile(const UmmaParams& p, int mt, int n
                 if (!ok[i]) continue;
                 if (EPI == EPI_STORE16 || EPI == EPI_GELU16) {
                     a.x += bias4.x; a.y += bias4.y; a.z += bias4.z; a.w += bias4.w;
-                    if (EPI == EPI_GELU16) { a.x = gelu_erf(a.x); a.y = gelu_erf(a.y); a.z = gelu_erf(a.z); a.w = gelu_erf(a.w); }
+                    if (EPI == EPI_GELU16) {
+                        const float2 g0 = gelu_erf2(make_float2(a.x, a.y)), g1 = gelu_erf2(make_float2(a.z, a.w));
+                        a = make_float4(g0.x, g0.y, g1.x, g1.y);
+                    }
                     uint2 pk;
                     pk.x = H::pack(a.x, a.y); pk.y = H::pack(a.z, a.w);
                     *reinterpret_cast<uint2*>(static_cast<typename H::T*>(p.out0) + roff[i] + co) = pk;
