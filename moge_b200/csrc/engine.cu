@@ -478,6 +478,18 @@ static int add_conv(moge_engine* e, Plan* pl, const ConvW& cw, const void* src, 
         pl->ops.add([=](cudaStream_t st) { return launch_conv64(bn64, epi, bf16, ma, mx, mb, p, sms, st); }, name, flops, bytes);
         return 0;
     }
+    // C_in >= 128 3x3 convs (levels 1/2): halo boxes for the pixels + streamed weights (convh_kernel.cuh); MOGE_B200_CONVH=0 disables, =1 restricts it to 128-wide tiles
+    static const int convh_mode = [] { const char* v = getenv("MOGE_B200_CONVH"); return v ? atoi(v) : 2; }();
+    const bool useh = convh_mode != 0 && epi == EPI_DEC && cw.taps == 9 && cw.cin >= 128 && cw.cin % 64 == 0 && cw.caux % 64 == 0 &&
+                      gs.Hp >= 10 && (bn == 128 || (bn == 256 && convh_mode >= 2)) && convh_supports(bn, p);
+    if (useh) {
+        MG_TRY(make_map_nhwc(&ma, src, cw.cin, gs.Wp, gs.Hp, B, 10));
+        if (cw.caux) MG_TRY(make_map_nhwc(&mx, aux, cw.caux, gs.Wp, gs.Hp, B, 8));
+        else mx = ma;
+        MG_TRY(make_map_2d(&mb, cw.w, cw.Ktot, cw.N, cw.Ktot, bn));
+        pl->ops.add([=](cudaStream_t st) { return launch_convh(bn, bf16, ma, mx, mb, p, sms, st); }, name, flops, bytes);
+        return 0;
+    }
     MG_TRY(make_map_nhwc(&ma, src, cw.cin, gs.Wp, gs.Hp, B));
     if (cw.caux) MG_TRY(make_map_nhwc(&mx, aux, cw.caux, gs.Wp, gs.Hp, B));
     else mx = ma;
@@ -1034,6 +1046,11 @@ int moge_op_conv(const void* x, const float* w, const float* bias, const void* s
             rc = make_map_nhwc(&ma, x, Cin, gs.Wp, gs.Hp, B, 10);
             if (rc == 0) rc = make_map_2d(&mb, wp, Ktot, N, Ktot, 64);
             if (rc == 0) rc = launch_conv64(64, EPI_DEC, bf16, ma, ma, mb, p, dev_sms(), st);
+        } else if (taps == 9 && Cin >= 128 && gs.Hp >= 10 && convh_supports(bn, p) &&
+                   [&] { const char* v = getenv("MOGE_B200_CONVH"); const int m = v ? atoi(v) : 2; return m != 0 && (bn == 128 || m >= 2); }()) {
+            rc = make_map_nhwc(&ma, x, Cin, gs.Wp, gs.Hp, B, 10);
+            if (rc == 0) rc = make_map_2d(&mb, wp, Ktot, N, Ktot, bn);
+            if (rc == 0) rc = launch_convh(bn, bf16, ma, ma, mb, p, dev_sms(), st);
         } else {
             rc = make_map_nhwc(&ma, x, Cin, gs.Wp, gs.Hp, B);
             if (rc == 0) rc = make_map_2d(&mb, wp, Ktot, N, Ktot, bn);

@@ -40,6 +40,12 @@ int launch_umma2(int epi, bool bf16, const CUtensorMap& a, const CUtensorMap& b,
 int launch_conv64(int bn, int epi, bool bf16, const CUtensorMap& a, const CUtensorMap& aux, const CUtensorMap& w, const UmmaParams& p,
                   int num_sms, cudaStream_t st);
 
+// 3x3 conv with C_in >= 128 (levels 1-2): halo boxes {64,16,10} for the pixels, streamed weight blocks (convh_kernel.cuh);
+// a: box {64,16,10}, aux: box {64,16,8}, w: box {64, bn}
+bool convh_supports(int bn, const UmmaParams& p);
+int launch_convh(int bn, bool bf16, const CUtensorMap& a, const CUtensorMap& aux, const CUtensorMap& w, const UmmaParams& p, int num_sms,
+                 cudaStream_t st);
+
 // 3x3 conv with C_in = 64, operands swapped (weights on M = 64, 16x16 pixels on N = 256): convs_kernel.cuh
 int launch_convs(int epi, bool bf16, const CUtensorMap& a, const CUtensorMap& aux, const CUtensorMap& w, const UmmaParams& p, int num_sms,
                  cudaStream_t st);

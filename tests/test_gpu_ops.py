@@ -112,6 +112,16 @@ def test_conv3x3_replicate_skip_relu(B, H, W, Cin, Cout, dtype):
     assert border_ok(raw, H, W) and border_ok(relu, H, W)
 
 
+def test_conv3x3_halo_streamed_weights(monkeypatch):
+    """convh_kernel (C_in >= 128: halo boxes + streamed weights) for both tile widths, and the generic kernel it replaces."""
+    for mode in ("2", "0"):
+        monkeypatch.setenv("MOGE_B200_CONVH", mode)
+        for dtype in (torch.float16, torch.bfloat16):
+            test_conv3x3_replicate_skip_relu(2, 24, 40, 256, 256, dtype)
+            test_conv3x3_replicate_skip_relu(1, 37, 37, 128, 128, dtype)
+            test_conv3x3_replicate_skip_relu(1, 21, 50, 192, 128, dtype)
+
+
 def test_conv3x3_swapped_operands(monkeypatch):
     """Experimental convs_kernel (weights on the M side, 16x16 pixels on N = 256), enabled by MOGE_B200_CONVS=1."""
     monkeypatch.setenv("MOGE_B200_CONVS", "1")

@@ -15,7 +15,7 @@ def timeit(fn, iters=3):
     e1.record(); torch.cuda.synchronize()
     return e0.elapsed_time(e1) / iters
 if "conv" in what:
-    for (H, W, C, skip, both) in [(74, 74, 256, False, False), (74, 74, 256, True, True), (296, 296, 64, False, False), (296, 296, 64, True, True)]:
+    for (H, W, C, skip, both) in [(74, 74, 256, False, False), (74, 74, 256, True, True), (148, 148, 128, False, False), (148, 148, 128, True, True), (296, 296, 64, False, False), (296, 296, 64, True, True)]:
         Hp, Wp = H + 2, W + 2
         x = torch.randn(B, Hp, Wp, C, device=dev).half()
         w = (torch.randn(C, C, 3, 3, device=dev) / (9 * C) ** 0.5)
