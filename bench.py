@@ -261,21 +261,36 @@ def run_engine(a):
         t = sum(ms_op[i] for i in idx) / 1e3
         return idx, t, sum(ops[i][1] for i in idx), sum(ops[i][2] for i in idx)
 
+    # DRAM traffic of the dominant launch of each class, from the committed `ncu --set full` capture of this workload
+    # (profiles/r1_ncu_traffic.json; per launch, like `achieved`); null for any other workload
+    traffic = {}
+    tpath = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r1_ncu_traffic.json")
+    if a.size == "vitl" and B == 32 and R == 518 and a.tokens == 1369 and a.dtype == "fp16" and os.path.exists(tpath):
+        with open(tpath) as fh:
+            traffic = json.load(fh)
+
+    def traffic_of(key):
+        t_ = traffic.get(key)
+        return (None, None) if not t_ else (t_["dram_bytes"], {"kernel": t_["kernel"], "algorithmic_bytes": t_["algorithmic_bytes"],
+                                                                "ratio_to_algorithmic": t_["dram_bytes"] / t_["algorithmic_bytes"], "source": t_["file"]})
+
     total_prof_ms = sum(ms_op)
     idx, t, fl, by = cls(("gemm.",))
     roofline = {"kernel": "umma2_kernel (cta_group::2) + umma_kernel<AMODE_ROWS>: encoder linears patch/qkv/proj/fc1/fc2/taps", "bound": "tensor",
                 "achieved": fl / t / 1e12, "peak": pk["tflops"], "unit": "TFLOP/s", "frac": fl / t / 1e12 / pk["tflops"],
-                "traffic": None, "launches": len(idx), "ms_per_step": t * 1e3, "share_of_step": t * 1e3 / total_prof_ms,
-                "peak_source": pk["source"]}
+                "traffic": traffic_of("gemm")[0], "traffic_detail": traffic_of("gemm")[1], "launches": len(idx), "ms_per_step": t * 1e3,
+                "share_of_step": t * 1e3 / total_prof_ms, "peak_source": pk["source"]}
     idx, t, fl, by = cls(("conv",))
     dec_bound_s = max(fl / (pk["tflops"] * 1e12), by / (pk["hbm_gbs"] * 1e9))
     roofline_decoder = {"kernel": "umma_kernel<AMODE_TILES> + conv64_kernel (implicit-GEMM convs)", "bound": "hbm",
                         "achieved": by / t / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": by / t / 1e9 / pk["hbm_gbs"],
-                        "tensor_tflops": fl / t / 1e12, "frac_of_max_bound": dec_bound_s / t, "traffic": None, "launches": len(idx),
+                        "tensor_tflops": fl / t / 1e12, "frac_of_max_bound": dec_bound_s / t, "traffic": traffic_of("decoder")[0],
+                        "traffic_detail": traffic_of("decoder")[1], "launches": len(idx),
                         "ms_per_step": t * 1e3, "share_of_step": t * 1e3 / total_prof_ms}
     idx, t, fl, by = cls(("attention",))
     roofline_attention = {"kernel": "attention_kernel", "bound": "tensor", "achieved": fl / t / 1e12, "peak": pk["tflops"],
-                          "unit": "TFLOP/s", "frac": fl / t / 1e12 / pk["tflops"], "launches": len(idx), "ms_per_step": t * 1e3,
+                          "unit": "TFLOP/s", "frac": fl / t / 1e12 / pk["tflops"], "traffic": traffic_of("attention")[0],
+                          "traffic_detail": traffic_of("attention")[1], "launches": len(idx), "ms_per_step": t * 1e3,
                           "share_of_step": t * 1e3 / total_prof_ms}
     other_ms = total_prof_ms - roofline["ms_per_step"] - roofline_decoder["ms_per_step"] - roofline_attention["ms_per_step"]
 
