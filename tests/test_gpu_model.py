@@ -207,6 +207,24 @@ def test_batch_chunking_is_transparent():
         assert torch.equal(full[k], chunked[k]), k
 
 
+def test_serving_pipeline_matches_direct_infer():
+    """moge_b200.serving.InferPipeline (H2D | infer | D2H on three streams, double-buffered) returns exactly what direct
+    infer() calls return, for more batches than pipeline slots."""
+    from moge_b200.serving import InferPipeline
+    model, cfg, sd = get_model("vits", True, 1)
+    batches = [synthetic_images(3, 70, 98, 100 + i).pin_memory() for i in range(5)]
+    direct = [{k: v.cpu() for k, v in model.infer(b.to(DEV), num_tokens=100).items()} for b in batches]
+    torch.cuda.synchronize()
+    outs = [{k: torch.empty(v.shape, dtype=v.dtype).pin_memory() for k, v in direct[0].items()} for _ in batches]
+    pipe = InferPipeline(model, depth=2, num_tokens=100)
+    for b, o in zip(batches, outs):
+        pipe.submit(b, o)
+    pipe.join()
+    for d, o in zip(direct, outs):
+        for k in d:
+            assert torch.equal(d[k], o[k]), k
+
+
 def test_known_fov_branch_matches_port():
     model, cfg, sd = get_model("vits", True, 1)
     img = synthetic_images(2, 84, 112, 22)
