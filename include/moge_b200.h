@@ -111,6 +111,12 @@ int moge_postprocess(float* points, const float* normal_in, const float* mask_pr
  * 2 = out32[M,N] += gamma * (acc + bias).  x, w: 16-bit (dtype MOGE_F16/MOGE_BF16), K % 8 == 0, N % 128 == 0.       */
 int moge_op_linear(const void* x, const void* w, const float* bias, const float* gamma, void* out, int M, int N, int K,
                    int epi, int dtype, void* stream);
+/* y16[M,N] = epilogue(LayerNorm_eps1e-6(x32[M,K]; ln_gamma, ln_beta) @ w32[N,K]^T + bias), epi 0 or 1 as above, computed the way the
+ * engine computes norm1->qkv and norm2->fc1 (dinov2/layers/block.py:84-92): the GEMM runs on the ROUNDED rows with the centred
+ * weight W diag(gamma) (I - 11^T/K) (mean removal is linear), the epilogue scales by rstd[row] and adds b + W beta.
+ * This is the engine's MOGE_B200_LNFOLD=1 path.  K % 64 == 0, N % 128 == 0.                                               */
+int moge_op_linear_ln(const float* x, const float* ln_gamma, const float* ln_beta, const float* w, const float* bias, void* out, int M,
+                      int N, int K, int epi, int dtype, void* stream);
 /* softmax(q k^T / 8) v per head on a fused qkv buffer (B,N,3*D) -> (B,N,D); D = heads*64 (attention.py:70-81) */
 int moge_op_attention(const void* qkv, void* out, int B, int N, int D, int heads, int dtype, void* stream);
 /* LayerNorm(eps=1e-6) of fp32 rows -> 16-bit */

@@ -20,7 +20,7 @@ RESAMPLE = {"conv_transpose": 0, "bilinear": 1}
 EXPORTS = [
     "moge_last_error", "moge_version", "moge_engine_create", "moge_engine_destroy", "moge_engine_set_weight",
     "moge_engine_finalize", "moge_engine_workspace_bytes", "moge_engine_forward", "moge_engine_num_ops", "moge_engine_op_info", "moge_engine_profile", "moge_recover_focal_shift",
-    "moge_postprocess", "moge_op_linear", "moge_op_attention", "moge_op_layernorm", "moge_op_conv",
+    "moge_postprocess", "moge_op_linear", "moge_op_linear_ln", "moge_op_attention", "moge_op_layernorm", "moge_op_conv",
 ]
 
 
@@ -75,6 +75,7 @@ def lib() -> C.CDLL:
     L.moge_recover_focal_shift.argtypes = [vp, vp, vp, ci, ci, ci, vp, vp, vp, vp]
     L.moge_postprocess.argtypes = [vp, vp, vp, vp, vp, vp, ci, ci, ci, ci, ci, vp, vp, vp, vp, vp]
     L.moge_op_linear.argtypes = [vp, vp, vp, vp, vp, ci, ci, ci, ci, ci, vp]
+    L.moge_op_linear_ln.argtypes = [vp, vp, vp, vp, vp, vp, ci, ci, ci, ci, ci, vp]
     L.moge_op_attention.argtypes = [vp, vp, ci, ci, ci, ci, ci, vp]
     L.moge_op_layernorm.argtypes = [vp, vp, vp, vp, ci, ci, ci, vp]
     L.moge_op_conv.argtypes = [vp, vp, vp, vp, vp, vp, ci, ci, ci, ci, ci, ci, ci, ci, vp]

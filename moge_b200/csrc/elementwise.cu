@@ -159,6 +159,106 @@ int launch_init_cls(float* x, const float* cls_row, int B, int N, int D, cudaStr
     return 0;
 }
 
+// ------------------------------------------------------------------------------------------ LayerNorm folded into the next GEMM
+// LN(x) W^T + b = rstd * ((x - mu 1) W'^T) + b' = rstd * (x W''^T) + b'
+//   with  W' = W diag(gamma),  W'' = W' (I - 1 1^T / D)  (every row of W' centred: the mean removal is a linear map and lives
+//   in the weight),  b' = b + W beta.
+// The GEMM consumes the ROUNDED residual rows x16 directly and its epilogue only scales by rstd[row] and adds b' -- the same
+// instruction count as a plain bias epilogue (these epilogues run neck and neck with the MMAs: an explicit rank-1 mean
+// correction in the epilogue measured +30 % on the qkv / fc1 GEMMs).  rstd comes from per-row partial sums (sum, sum of squares
+// of the rounded values) that the producing epilogue (patch embed, proj, fc2) writes next to x16, reduced by ln_rstd_kernel.
+// Rounding W'' to 16 bit leaves a column-sum residual of ~sqrt(D) * 2^-11 * |W''|: the mean is removed to that relative
+// precision, which is below the 16-bit rounding of the activations for |mu| <~ 10 sigma.
+template <bool BF16>
+__global__ void ln_prepare_kernel(const float* __restrict__ x, long row_stride, int D, typename H16<BF16>::T* __restrict__ x16,
+                                  long row_stride16, float2* __restrict__ stats, long stats_stride, int parts) {
+    using H = H16<BF16>;
+    const long r = blockIdx.x;
+    const float* xr = x + r * row_stride;
+    float s1 = 0.f, s2 = 0.f;
+    for (int d = 2 * threadIdx.x; d < D; d += 2 * blockDim.x) {
+        const uint32_t pk = H::pack(xr[d], xr[d + 1]);
+        *reinterpret_cast<uint32_t*>(x16 + r * row_stride16 + d) = pk;
+        const float2 f = H::unpack(pk);
+        s1 += f.x + f.y; s2 += f.x * f.x + f.y * f.y;
+    }
+    __shared__ float red[2][32];
+    for (int o = 16; o > 0; o >>= 1) { s1 += __shfl_xor_sync(0xffffffffu, s1, o); s2 += __shfl_xor_sync(0xffffffffu, s2, o); }
+    if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = s1; red[1][threadIdx.x >> 5] = s2; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float a = 0.f, b = 0.f;
+        for (int w = 0; w < (blockDim.x >> 5); ++w) { a += red[0][w]; b += red[1][w]; }
+        stats[r * stats_stride] = make_float2(a, b);
+        for (int pp = 1; pp < parts; ++pp) stats[r * stats_stride + pp] = make_float2(0.f, 0.f);
+    }
+}
+int launch_ln_prepare(const float* x, int rows, long row_stride, int D, void* x16, long row_stride16, float2* stats, long stats_stride,
+                      int parts, bool bf16, cudaStream_t st) {
+    if (D % 2) return set_error("ln_prepare: D must be even");
+    if (rows <= 0) return 0;
+    if (bf16) ln_prepare_kernel<true><<<rows, 128, 0, st>>>(x, row_stride, D, static_cast<__nv_bfloat16*>(x16), row_stride16, stats, stats_stride, parts);
+    else ln_prepare_kernel<false><<<rows, 128, 0, st>>>(x, row_stride, D, static_cast<__half*>(x16), row_stride16, stats, stats_stride, parts);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+// per-row rstd from the partial sums: rstd[r] = 1 / sqrt(E[x^2] - E[x]^2 + 1e-6)
+__global__ void ln_rstd_kernel(const float2* __restrict__ stats, int ld, int parts, int rows, float inv_d, float* __restrict__ rstd) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= rows) return;
+    float a = 0.f, b = 0.f;
+    for (int pp = 0; pp < parts; ++pp) { const float2 t = stats[static_cast<size_t>(r) * ld + pp]; a += t.x; b += t.y; }
+    const float mean = a * inv_d;
+    rstd[r] = rsqrtf(fmaxf(b * inv_d - mean * mean, 0.f) + 1e-6f);
+}
+int launch_ln_rstd(const float2* stats, int ld, int parts, int rows, int D, float* rstd, cudaStream_t st) {
+    if (rows <= 0) return 0;
+    ln_rstd_kernel<<<(rows + 255) / 256, 256, 0, st>>>(stats, ld, parts, rows, 1.0f / static_cast<float>(D), rstd);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+// one block per output feature n: c = mean_k(W[n,k] gamma[k]);  w16[n,k] = T(W[n,k] gamma[k] - c);  b2[n] = b[n] + sum_k W[n,k] beta[k]
+template <bool BF16>
+__global__ void ln_fold_kernel(const float* __restrict__ W, const float* __restrict__ gamma, const float* __restrict__ beta,
+                               const float* __restrict__ bias, int K, int ldw, typename H16<BF16>::T* __restrict__ w16,
+                               float* __restrict__ b2) {
+    using H = H16<BF16>;
+    const int n = blockIdx.x;
+    float s = 0.f, t = 0.f;
+    for (int k = threadIdx.x; k < K; k += blockDim.x) {
+        const float w = W[static_cast<size_t>(n) * K + k];
+        s += w * gamma[k];
+        t += w * beta[k];
+    }
+    __shared__ float red[2][32];
+    __shared__ float centre;
+    for (int o = 16; o > 0; o >>= 1) { s += __shfl_xor_sync(0xffffffffu, s, o); t += __shfl_xor_sync(0xffffffffu, t, o); }
+    if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = s; red[1][threadIdx.x >> 5] = t; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float a = 0.f, b = 0.f;
+        for (int w = 0; w < (blockDim.x >> 5); ++w) { a += red[0][w]; b += red[1][w]; }
+        centre = a / static_cast<float>(K);
+        b2[n] = (bias ? bias[n] : 0.f) + b;
+    }
+    __syncthreads();
+    const float c = centre;
+    for (int k = 2 * threadIdx.x; k < K; k += 2 * blockDim.x) {
+        const float w0 = W[static_cast<size_t>(n) * K + k], w1 = W[static_cast<size_t>(n) * K + k + 1];
+        *reinterpret_cast<uint32_t*>(w16 + static_cast<size_t>(n) * ldw + k) = H::pack(w0 * gamma[k] - c, w1 * gamma[k + 1] - c);
+    }
+}
+int launch_ln_fold(const float* W, const float* gamma, const float* beta, const float* bias, int N, int K, int ldw, void* w16,
+                   float* b2, bool bf16, cudaStream_t st) {
+    if (K % 2) return set_error("ln_fold: K must be even");
+    if (bf16) ln_fold_kernel<true><<<N, 128, 0, st>>>(W, gamma, beta, bias, K, ldw, static_cast<__nv_bfloat16*>(w16), b2);
+    else ln_fold_kernel<false><<<N, 128, 0, st>>>(W, gamma, beta, bias, K, ldw, static_cast<__half*>(w16), b2);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
 // ------------------------------------------------------------------------------------------ LayerNorm
 // torch LayerNorm (biased variance, eps 1e-6; vision_transformer.py:95) on the fp32 residual stream -> 16-bit GEMM
 // operand.  One warp per row, row held in registers (D <= 1024), two-pass statistics by warp shuffles.

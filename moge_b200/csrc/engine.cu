@@ -102,7 +102,13 @@ struct moge_engine {
     std::vector<void*> owned;         // cudaMalloc'd, freed at destroy
     // packed encoder
     void* w_patch = nullptr;
-    struct Blk { void *wqkv, *wproj, *wfc1, *wfc2; const float *bqkv, *bproj, *bfc1, *bfc2, *g1, *g2, *ln1g, *ln1b, *ln2g, *ln2b; };
+    struct Blk {
+        void *wqkv, *wproj, *wfc1, *wfc2;
+        const float *bqkv, *bproj, *bfc1, *bfc2, *g1, *g2, *ln1g, *ln1b, *ln2g, *ln2b;
+        // LayerNorm folded into the GEMM (MOGE_B200_LNFOLD=1): centred W diag(gamma) in 16 bit, b + W beta
+        void *wqkv_ln, *wfc1_ln;
+        float *b_qkv_ln, *b_fc1_ln;
+    };
     std::vector<Blk> blk;
     const float *norm_g = nullptr, *norm_b = nullptr, *pos_embed = nullptr, *cls_token = nullptr, *patch_bias = nullptr;
     ConvW fold0;                      // taps-concat GEMM: (output projections folded into neck.input_blocks.0)
@@ -112,6 +118,7 @@ struct moge_engine {
     Plan* last_plan = nullptr;
     bool use_graphs = true;
     bool use_2cta = false;
+    bool ln_fold = false;         // MOGE_B200_LNFOLD=1: LayerNorm folded into qkv / fc1 (default: separate layernorm kernel)
     cudaStream_t own_stream = nullptr;
     cudaEvent_t ev_in = nullptr, ev_out = nullptr;
 
@@ -349,6 +356,17 @@ static int finalize(moge_engine* e, cudaStream_t st) {
         MG_TRY(vec(e, p + "norm1.bias", D, &b.ln1b));
         MG_TRY(vec(e, p + "norm2.weight", D, &b.ln2g));
         MG_TRY(vec(e, p + "norm2.bias", D, &b.ln2b));
+        if (e->ln_fold) {
+            const RawWeight *wq, *wf;
+            MG_TRY(get_raw(e, p + "attn.qkv.weight", &wq, {}));
+            MG_TRY(get_raw(e, p + "mlp.fc1.weight", &wf, {}));
+            MG_TRY(e->alloc(&b.wqkv_ln, static_cast<size_t>(3 * D) * D * 2));
+            MG_TRY(e->alloc(&b.wfc1_ln, static_cast<size_t>(4 * D) * D * 2));
+            MG_TRY(e->alloc(reinterpret_cast<void**>(&b.b_qkv_ln), static_cast<size_t>(3 * D) * 4));
+            MG_TRY(e->alloc(reinterpret_cast<void**>(&b.b_fc1_ln), static_cast<size_t>(4 * D) * 4));
+            MG_TRY(launch_ln_fold(wq->p, b.ln1g, b.ln1b, b.bqkv, 3 * D, D, D, b.wqkv_ln, b.b_qkv_ln, e->bf16, st));
+            MG_TRY(launch_ln_fold(wf->p, b.ln2g, b.ln2b, b.bfc1, 4 * D, D, D, b.wfc1_ln, b.b_fc1_ln, e->bf16, st));
+        }
     }
     // ---- fold: neck.input_blocks.0 o (sum_j output_projections.j)  ->  one GEMM over the concatenated taps
     {
@@ -498,8 +516,16 @@ static int add_conv(moge_engine* e, Plan* pl, const ConvW& cw, const void* src, 
     return 0;
 }
 
+constexpr int kStatsLd = 16;      // partial-sum slots per row of the LayerNorm statistics buffer
+struct LnIO {                     // LayerNorm-fold plumbing of one linear (see elementwise.cu)
+    void* x16 = nullptr;          // producer (EPI_RESID / EPI_PATCH): 16-bit copy of the rows it writes
+    float2* stats_out = nullptr;  // producer: partial sums
+    int* parts_out = nullptr;     // producer: number of column groups it writes per row
+    const float* ln_rstd = nullptr;       // consumer (EPI_STORE16 / EPI_GELU16)
+};
 static int add_linear(moge_engine* e, Plan* pl, const void* A, int M, int K, int lda, const void* W, int N, int epi,
-                      void* out, const float* bias, const float* v1, int ldo, const char* name, int T = 0, int gridw = 0) {
+                      void* out, const float* bias, const float* v1, int ldo, const char* name, int T = 0, int gridw = 0,
+                      const LnIO* ln = nullptr) {
     UmmaParams p{};
     p.M = M; p.N = N; p.ntaps = 1; p.kb_main = (K + 63) / 64; p.kb_aux = 0;
     p.num_m_tiles = (M + TILE_M - 1) / TILE_M;
@@ -509,13 +535,25 @@ static int add_linear(moge_engine* e, Plan* pl, const void* A, int M, int K, int
     if (bn == 256 && p.num_m_tiles * (N / 256) * 4 < e->num_sms * 3) bn = 128;
     p.num_n_tiles = N / bn;
     p.out0 = out; p.bias = bias; p.vec1 = v1; p.ldo = ldo; p.T = T; p.W = gridw;
+    double ln_extra_bytes = 0;
+    if (ln) {
+        const int parts = N / (bn / 2);             // every ROWS kernel has 8 epilogue warps: column groups of BN/2
+        p.stats_ld = kStatsLd;
+        if (ln->x16) {
+            if (parts > kStatsLd) return set_error("linear %s: %d statistics groups per row > %d", name, parts, kStatsLd);
+            p.x16 = ln->x16; p.stats_out = ln->stats_out;
+            if (ln->parts_out) *ln->parts_out = parts;
+            ln_extra_bytes = static_cast<double>(M) * N * 2;
+        }
+        if (ln->ln_rstd) p.ln_rstd = ln->ln_rstd;
+    }
     CUtensorMap ma, mb;
     MG_TRY(make_map_2d(&ma, A, K, M, lda, TILE_M));
     const bool bf16 = e->bf16; const int sms = e->num_sms;
     const double flops2 = 2.0 * M * static_cast<double>(N) * K;
     if (bn == 256 && e->use_2cta && (epi == EPI_STORE16 || epi == EPI_GELU16 || epi == EPI_RESID)) {
         MG_TRY(make_map_2d(&mb, W, K, N, lda, 128));
-        double bytes2 = static_cast<double>(M) * K * 2 + static_cast<double>(N) * K * 2 + ((epi == EPI_RESID) ? static_cast<double>(M) * N * 8 : static_cast<double>(M) * N * 2);
+        double bytes2 = static_cast<double>(M) * K * 2 + static_cast<double>(N) * K * 2 + ((epi == EPI_RESID) ? static_cast<double>(M) * N * 8 : static_cast<double>(M) * N * 2) + ln_extra_bytes;
         pl->ops.add([=](cudaStream_t st) { return launch_umma2(epi, bf16, ma, mb, p, sms, st); }, name, flops2, bytes2);
         return 0;
     }
@@ -524,6 +562,7 @@ static int add_linear(moge_engine* e, Plan* pl, const void* A, int M, int K, int
     double bytes = static_cast<double>(M) * K * 2 + static_cast<double>(N) * K * 2;
     bytes += (epi == EPI_RESID) ? static_cast<double>(M) * N * 8 : (epi == EPI_PATCH) ? static_cast<double>(M) * N * 4 + static_cast<double>(T) * N * 4
                                                                                       : static_cast<double>(M) * N * 2;
+    bytes += ln_extra_bytes;
     pl->ops.add([=](cudaStream_t st) { return launch_umma(bn, AMODE_ROWS, epi, bf16, ma, ma, mb, p, sms, st); }, name, flops, bytes);
     return 0;
 }
@@ -596,7 +635,9 @@ static int build_plan(moge_engine* e, Plan* pl, bool dry, size_t* bytes_out) {
     // ---- encoder buffers
     void* patches = ws.take(static_cast<size_t>(B) * T * 592 * 2);
     float* x = static_cast<float*>(ws.take(static_cast<size_t>(M) * D * 4));
-    void* ln = ws.take(static_cast<size_t>(M) * D * 2);
+    void* ln = ws.take(static_cast<size_t>(M) * D * 2);          // LN output, or (LN fold) the rounded residual rows x16
+    float2* stats = static_cast<float2*>(ws.take(static_cast<size_t>(M) * kStatsLd * 8));
+    float* rstd = static_cast<float*>(ws.take(static_cast<size_t>(M) * 4));
     void* qkv = ws.take(static_cast<size_t>(M) * 3 * D * 2);
     void* att = ws.take(static_cast<size_t>(M) * D * 2);
     void* hid = ws.take(static_cast<size_t>(M) * 4 * D * 2);
@@ -644,15 +685,34 @@ static int build_plan(moge_engine* e, Plan* pl, bool dry, size_t* bytes_out) {
     pl->ops.add([=](cudaStream_t st) { return launch_preprocess(P->image, P->image_dtype, B, H, W, h, w, patches, 592, bf16, st); },
                 "preprocess", 0, static_cast<double>(B) * 3 * H * W * 4 + static_cast<double>(B) * T * 592 * 2);
     // ---- K2/K3: patch embed + pos embed; cls rows
-    MG_TRY(add_linear(e, pl, patches, B * T, 592, 592, e->w_patch, D, EPI_PATCH, x, nullptr, pl->pos_table, D, "gemm.patch_embed", T, w));
+    const bool fold = e->ln_fold;
+    int parts_x = 0;              // column groups per row of the statistics the NEXT consumer reads
+    LnIO prod; prod.x16 = ln; prod.stats_out = stats; prod.parts_out = &parts_x;
+    MG_TRY(add_linear(e, pl, patches, B * T, 592, 592, e->w_patch, D, EPI_PATCH, x, nullptr, pl->pos_table, D, "gemm.patch_embed", T, w,
+                      fold ? &prod : nullptr));
     pl->ops.add([=](cudaStream_t st) { return launch_init_cls(x, P->cls_row, B, N, D, st); }, "init_cls");
+    if (fold) {
+        const int parts0 = parts_x;
+        pl->ops.add([=](cudaStream_t st) {
+            return launch_ln_prepare(x, B, static_cast<long>(N) * D, D, ln, static_cast<long>(N) * D, stats, static_cast<long>(N) * kStatsLd, parts0, bf16, st);
+        }, "ln_prepare.cls");
+    }
+    auto add_rstd = [&](int parts) {      // per-row rstd of the rows the last producer wrote
+        pl->ops.add([=](cudaStream_t st) { return launch_ln_rstd(stats, kStatsLd, parts, M, D, rstd, st); }, "ln_rstd", 0, static_cast<double>(M) * (parts * 8 + 4));
+    };
     // ---- transformer blocks
     int tap_idx = 0;
     for (int i = 0; i < c.depth; ++i) {
         const moge_engine::Blk& b = e->blk[i];
         const double ln_bytes = static_cast<double>(M) * D * 6;
-        pl->ops.add([=](cudaStream_t st) { return launch_layernorm(x, b.ln1g, b.ln1b, ln, M, D, D, 0, 0, N, nullptr, bf16, st); }, "layernorm", 0, ln_bytes);
-        MG_TRY(add_linear(e, pl, ln, M, D, D, b.wqkv, 3 * D, EPI_STORE16, qkv, b.bqkv, nullptr, 3 * D, "gemm.qkv"));
+        if (fold) {
+            if (i == 0) add_rstd(parts_x);
+            LnIO cons; cons.ln_rstd = rstd;
+            MG_TRY(add_linear(e, pl, ln, M, D, D, b.wqkv_ln, 3 * D, EPI_STORE16, qkv, b.b_qkv_ln, nullptr, 3 * D, "gemm.qkv", 0, 0, &cons));
+        } else {
+            pl->ops.add([=](cudaStream_t st) { return launch_layernorm(x, b.ln1g, b.ln1b, ln, M, D, D, 0, 0, N, nullptr, bf16, st); }, "layernorm", 0, ln_bytes);
+            MG_TRY(add_linear(e, pl, ln, M, D, D, b.wqkv, 3 * D, EPI_STORE16, qkv, b.bqkv, nullptr, 3 * D, "gemm.qkv"));
+        }
         {
             CUtensorMap mq;
             MG_TRY(make_map_3d(&mq, qkv, 3 * D, N, B, 128));
@@ -660,10 +720,19 @@ static int build_plan(moge_engine* e, Plan* pl, bool dry, size_t* bytes_out) {
             pl->ops.add([=](cudaStream_t st) { return launch_attention(mq, att, B, N, D, heads, bf16, st); }, "attention",
                         4.0 * B * static_cast<double>(N) * N * D, static_cast<double>(M) * D * 8);
         }
-        MG_TRY(add_linear(e, pl, att, M, D, D, b.wproj, D, EPI_RESID, x, b.bproj, b.g1, D, "gemm.proj"));
-        pl->ops.add([=](cudaStream_t st) { return launch_layernorm(x, b.ln2g, b.ln2b, ln, M, D, D, 0, 0, N, nullptr, bf16, st); }, "layernorm", 0, ln_bytes);
-        MG_TRY(add_linear(e, pl, ln, M, D, D, b.wfc1, 4 * D, EPI_GELU16, hid, b.bfc1, nullptr, 4 * D, "gemm.fc1"));
-        MG_TRY(add_linear(e, pl, hid, M, 4 * D, 4 * D, b.wfc2, D, EPI_RESID, x, b.bfc2, b.g2, D, "gemm.fc2"));
+        if (fold) {
+            MG_TRY(add_linear(e, pl, att, M, D, D, b.wproj, D, EPI_RESID, x, b.bproj, b.g1, D, "gemm.proj", 0, 0, &prod));
+            add_rstd(parts_x);
+            LnIO cons; cons.ln_rstd = rstd;
+            MG_TRY(add_linear(e, pl, ln, M, D, D, b.wfc1_ln, 4 * D, EPI_GELU16, hid, b.b_fc1_ln, nullptr, 4 * D, "gemm.fc1", 0, 0, &cons));
+            MG_TRY(add_linear(e, pl, hid, M, 4 * D, 4 * D, b.wfc2, D, EPI_RESID, x, b.bfc2, b.g2, D, "gemm.fc2", 0, 0, (i + 1 < c.depth) ? &prod : nullptr));
+            if (i + 1 < c.depth) add_rstd(parts_x);
+        } else {
+            MG_TRY(add_linear(e, pl, att, M, D, D, b.wproj, D, EPI_RESID, x, b.bproj, b.g1, D, "gemm.proj"));
+            pl->ops.add([=](cudaStream_t st) { return launch_layernorm(x, b.ln2g, b.ln2b, ln, M, D, D, 0, 0, N, nullptr, bf16, st); }, "layernorm", 0, ln_bytes);
+            MG_TRY(add_linear(e, pl, ln, M, D, D, b.wfc1, 4 * D, EPI_GELU16, hid, b.bfc1, nullptr, 4 * D, "gemm.fc1"));
+            MG_TRY(add_linear(e, pl, hid, M, 4 * D, 4 * D, b.wfc2, D, EPI_RESID, x, b.bfc2, b.g2, D, "gemm.fc2"));
+        }
         if (tap_idx < c.num_taps && c.taps[tap_idx] == i) {
             const int j = tap_idx++;
             const bool lasttap = (j == c.num_taps - 1);
@@ -797,6 +866,8 @@ int moge_engine_create(const moge_config_t* cfg, int device, moge_engine_t** out
     e->use_graphs = !(env && env[0] == '0');
     const char* env2 = getenv("MOGE_B200_2CTA");
     e->use_2cta = !(env2 != nullptr && env2[0] == '0');
+    const char* env3 = getenv("MOGE_B200_LNFOLD");
+    e->ln_fold = env3 != nullptr && env3[0] == '1';
     if (cudaStreamCreateWithFlags(&e->own_stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreateWithFlags(&e->ev_in, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&e->ev_out, cudaEventDisableTiming) != cudaSuccess) {
@@ -1002,6 +1073,47 @@ int moge_op_attention(const void* qkv, void* out, int B, int N, int D, int heads
     CUtensorMap mq;
     MG_TRY(make_map_3d(&mq, qkv, 3 * static_cast<uint64_t>(D), N, B, 128));
     return launch_attention(mq, out, B, N, D, heads, dtype == MOGE_BF16, static_cast<cudaStream_t>(stream));
+}
+
+int moge_op_linear_ln(const float* x, const float* ln_gamma, const float* ln_beta, const float* w, const float* bias, void* out, int M,
+                      int N, int K, int epi, int dtype, void* stream) {
+    // out = epi(LayerNorm(x) W^T + bias) the way the engine computes it: rounded rows + row statistics, folded weights, one GEMM
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const bool bf16 = dtype == MOGE_BF16;
+    if (K % 64) return set_error("op_linear_ln: K must be a multiple of 64");
+    const int bn = pick_bn(N, {256, 128});
+    if (!bn) return set_error("op_linear_ln: N must be a multiple of 128");
+    if (epi != EPI_STORE16 && epi != EPI_GELU16) return set_error("op_linear_ln: epi must be 0 (store) or 1 (GELU)");
+    void *x16 = nullptr, *w16 = nullptr;
+    float2* stats = nullptr;
+    float *rstd = nullptr, *b2 = nullptr;
+    int rc = 0;
+    if (cudaMalloc(&x16, static_cast<size_t>(M) * K * 2) != cudaSuccess || cudaMalloc(&w16, static_cast<size_t>(N) * K * 2) != cudaSuccess ||
+        cudaMalloc(&stats, static_cast<size_t>(M) * kStatsLd * 8) != cudaSuccess || cudaMalloc(&rstd, static_cast<size_t>(M) * 4) != cudaSuccess ||
+        cudaMalloc(&b2, static_cast<size_t>(N) * 4) != cudaSuccess)
+        rc = set_error("op_linear_ln: cudaMalloc failed");
+    if (rc == 0) rc = launch_ln_prepare(x, M, K, K, x16, K, stats, kStatsLd, 1, bf16, st);
+    if (rc == 0) rc = launch_ln_rstd(stats, kStatsLd, 1, M, K, rstd, st);
+    if (rc == 0) rc = launch_ln_fold(w, ln_gamma, ln_beta, bias, N, K, K, w16, b2, bf16, st);
+    if (rc == 0) {
+        UmmaParams p{};
+        p.M = M; p.N = N; p.ntaps = 1; p.kb_main = K / 64;
+        p.num_m_tiles = (M + TILE_M - 1) / TILE_M; p.num_n_tiles = N / bn;
+        p.out0 = out; p.bias = b2; p.ldo = N;
+        p.ln_rstd = rstd;
+        CUtensorMap ma, mb;
+        rc = make_map_2d(&ma, x16, K, M, K, TILE_M);
+        if (rc == 0 && bn == 256 && use_2cta()) {
+            rc = make_map_2d(&mb, w16, K, N, K, 128);
+            if (rc == 0) rc = launch_umma2(epi, bf16, ma, mb, p, dev_sms(), st);
+        } else if (rc == 0) {
+            rc = make_map_2d(&mb, w16, K, N, K, bn);
+            if (rc == 0) rc = launch_umma(bn, AMODE_ROWS, epi, bf16, ma, ma, mb, p, dev_sms(), st);
+        }
+    }
+    cudaStreamSynchronize(st);
+    cudaFree(x16); cudaFree(w16); cudaFree(stats); cudaFree(rstd); cudaFree(b2);
+    return rc;
 }
 
 int moge_op_layernorm(const float* x, const float* gamma, const float* beta, void* out, int rows, int D, int dtype, void* stream) {

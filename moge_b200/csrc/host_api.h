@@ -65,6 +65,13 @@ int launch_init_cls(float* x, const float* cls_row, int B, int N, int D, cudaStr
 // the cls row of each image is written (fp32) to cls_out[b, D] when cls_out != null.
 int launch_layernorm(const float* x, const float* gamma, const float* beta, void* out, int rows, int D, int ld_out,
                      int col_off, int mode, int tokens_per_image, float* cls_out, bool bf16, cudaStream_t st);
+// LayerNorm folded into the following GEMM (see elementwise.cu): rounded rows + per-row partial sums for rows no GEMM epilogue
+// produces (cls rows; op-level tests), the per-row rstd reduction, and the load-time weight fold  w16 = T(rows of W diag(gamma), centred), b2 = b + W beta
+int launch_ln_prepare(const float* x, int rows, long row_stride, int D, void* x16, long row_stride16, float2* stats, long stats_stride,
+                      int parts, bool bf16, cudaStream_t st);
+int launch_ln_fold(const float* W, const float* gamma, const float* beta, const float* bias, int N, int K, int ldw, void* w16,
+                   float* b2, bool bf16, cudaStream_t st);
+int launch_ln_rstd(const float2* stats, int ld, int parts, int rows, int D, float* rstd, cudaStream_t st);
 // scale head: metric_scale[b] = exp(MLP(cls[b]))
 int launch_scale_head(const float* cls, const float* const* w, const float* const* bias, const int* dims, int nlayers,
                       int B, float* out, float* scratch, cudaStream_t st);

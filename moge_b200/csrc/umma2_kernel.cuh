@@ -159,14 +159,21 @@ umma2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
         const int col_begin = (ew >> 2) * (BN / 2);
         float4* scr = reinterpret_cast<float4*>(scratch_base + ew * 1024);
         int it = 0;
+        LnRows lnr{}, lnn{};
+        const bool ln_on = (EPI == EPI_STORE16 || EPI == EPI_GELU16) && p.ln_rstd != nullptr;
+        if (ln_on && pair < total) ln_load(p, 2 * (pair / p.num_n_tiles) + static_cast<int>(rank), quarter, lane, lnn);
         for (int t = pair; t < total; t += npairs, ++it) {
             const int mp = t / p.num_n_tiles, nt = t % p.num_n_tiles;
             const int mt = 2 * mp + static_cast<int>(rank);
             const int acc = it & 1;
+            if (ln_on) {        // rstd of this tile's rows (loaded one iteration ago); then issue the next tile's loads
+                lnr = lnn;
+                if (t + npairs < total) ln_load(p, 2 * ((t + npairs) / p.num_n_tiles) + static_cast<int>(rank), quarter, lane, lnn);
+            }
             mbar_wait(&tfull[acc], (it >> 1) & 1);
             tc_fence_after();
             const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN + col_begin;
-            epilogue_tile<BN, BN / 2, AMODE_ROWS, EPI, BF16>(p, mt, nt, t_addr, scr, quarter, lane, col_begin);
+            epilogue_tile<BN, BN / 2, AMODE_ROWS, EPI, BF16>(p, mt, nt, t_addr, scr, quarter, lane, col_begin, ln_on, lnr);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) {

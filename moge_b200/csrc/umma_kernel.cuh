@@ -58,6 +58,11 @@ struct UmmaParams {
     int shuffle;           // EPI_DEC: 1 = ConvTranspose2d k2s2 pixel shuffle (Ho = 2H, Wo = 2W), N = 4*C_out
     int ncomp;             // HEADOUT: 3 (float4 per pixel) or 1 (float per pixel)
     float su, sv;          // UV half extents
+    // LayerNorm folded into the consuming GEMM (ROWS epilogues; see elementwise.cu "LayerNorm folded into the next GEMM")
+    void* x16;                 // producers (EPI_RESID / EPI_PATCH): 16-bit copy of the rows written to out0 (pitch ldo), or null
+    float2* stats_out;         // producers: [row, stats_ld] partial (sum, sum of squares) of the ROUNDED row, one per column group
+    const float* ln_rstd;      // consumers (EPI_STORE16 / EPI_GELU16): 1/sqrt(var + eps) of the A rows; null = plain bias epilogue
+    int stats_ld;              // partial sums per row in stats_out
 };
 
 template <int BN> struct UmmaCfg {
@@ -113,6 +118,18 @@ static __device__ __noinline__ void store_px_border8(uint8_t* base, int b, int Y
     for (int dy = dy0; dy <= dy1; ++dy)
         for (int dx = dx0; dx <= dx1; ++dx)
             if (dy != 0 || dx != 0) *reinterpret_cast<uint2*>(centre + dy * rowp + dx * colp) = q;
+}
+
+// LayerNorm fold, consumer side: rstd of the 8 rows a lane serves after the transpose (row 4*i + sub of the warp's 32).  The
+// loads of tile i+1 are issued while tile i is drained and consumed one iteration later (no latency on the critical path).
+struct LnRows { float rs[8]; };
+__device__ __forceinline__ void ln_load(const UmmaParams& p, int mt, int quarter, int lane, LnRows& r) {
+    const int sub = lane >> 3;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const long grow = static_cast<long>(mt) * TILE_M + quarter * 32 + 4 * i + sub;
+        r.rs[i] = (grow < p.M) ? p.ln_rstd[grow] : 1.f;
+    }
 }
 
 // DF < 0: the EPI_DEC variant (raw / ReLU copies, skip, UV, pixel shuffle) is decided at run time from the params;
@@ -262,7 +279,7 @@ __device__ __forceinline__ void epilogue_dec16(const UmmaParams& p, int mt, int 
 
 template <int BN, int COLS, int AMODE, int EPI, bool BF16, int DF = -1>
 __device__ __forceinline__ void epilogue_tile(const UmmaParams& p, int mt, int nt, uint32_t t_addr, float4* scr, int quarter,
-                                              int lane, int col_begin) {
+                                              int lane, int col_begin, bool ln_rows_on = false, LnRows lnr = LnRows{}) {
     using H = H16<BF16>;
     const bool has_raw = (DF < 0) ? (p.out0 != nullptr) : ((DF & DF_RAW) != 0);
     const bool has_relu = (DF < 0) ? (p.out1 != nullptr) : ((DF & DF_RELU) != 0);
@@ -332,19 +349,24 @@ __device__ __forceinline__ void epilogue_tile(const UmmaParams& p, int mt, int n
         int rb[8], ry[8], rx[8];
         size_t roff[8];      // element offset of the row (ROWS epilogues) / BYTE offset of the centre output pixel (EPI_DEC)
         int eflags[8];       // EPI_DEC: bit0 y==0, bit1 y==H-1, bit2 x==0, bit3 x==W-1 (source grid)
+        int xrow[8];         // ROWS epilogues: row index in the output / statistics arrays
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
             const int rl = quarter * 32 + 4 * i + sub;
-            rb[i] = 0; ry[i] = 0; rx[i] = 0; roff[i] = 0; eflags[i] = 0;
+            rb[i] = 0; ry[i] = 0; rx[i] = 0; roff[i] = 0; eflags[i] = 0; xrow[i] = 0;
             if (AMODE == AMODE_ROWS) {
                 const long grow = static_cast<long>(mt) * TILE_M + rl;
                 ok[i] = grow < p.M;
+                xrow[i] = static_cast<int>(grow);
                 roff[i] = static_cast<size_t>(grow) * p.ldo;
                 if (EPI == EPI_DEC || EPI == EPI_PATCH) {
                     rb[i] = static_cast<int>(grow / p.T);
                     const int t = static_cast<int>(grow % p.T);
                     ry[i] = t / p.W; rx[i] = t % p.W;
-                    if (EPI == EPI_PATCH) roff[i] = (static_cast<size_t>(rb[i]) * (p.T + 1) + 1 + t) * p.ldo;
+                    if (EPI == EPI_PATCH) {
+                        xrow[i] = rb[i] * (p.T + 1) + 1 + t;
+                        roff[i] = static_cast<size_t>(xrow[i]) * p.ldo;
+                    }
                 }
             } else {
                 rb[i] = tile_b;
@@ -359,6 +381,15 @@ __device__ __forceinline__ void epilogue_tile(const UmmaParams& p, int mt, int n
             }
         }
         const float inv_wo = 1.0f / static_cast<float>(p.Wo), inv_ho = 1.0f / static_cast<float>(p.Ho);
+        // LayerNorm fold, consumer side: rstd and -rstd*mean of this lane's 8 rows from the producers' partial sums (the 8
+        // lanes that share a row split the partials, fixed order -> deterministic)
+        constexpr bool LN_CONS = (EPI == EPI_STORE16 || EPI == EPI_GELU16) && AMODE == AMODE_ROWS;
+        constexpr bool LN_PROD = (EPI == EPI_RESID || EPI == EPI_PATCH) && AMODE == AMODE_ROWS;
+        const bool ln_on = LN_CONS && ln_rows_on;
+        const bool x16_on = LN_PROD && p.x16 != nullptr;
+        float ln_rs[8], st1[8], st2[8];        // st1/st2 (producers): partial sums of x and x^2 of this lane's 8 rows
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { ln_rs[i] = ln_on ? lnr.rs[i] : 1.f; st1[i] = 0.f; st2[i] = 0.f; }
 #pragma unroll 1
         for (int c = 0; c < COLS; c += 32) {
             float v[32];
@@ -417,22 +448,44 @@ __device__ __forceinline__ void epilogue_tile(const UmmaParams& p, int mt, int n
                 float4 a = scr[rl * 8 + (q4 ^ (rl & 7))];
                 if (!ok[i]) continue;
                 if (EPI == EPI_STORE16 || EPI == EPI_GELU16) {
-                    a.x += bias4.x; a.y += bias4.y; a.z += bias4.z; a.w += bias4.w;
-                    if (EPI == EPI_GELU16) {
-                        const float2 g0 = gelu_erf2(make_float2(a.x, a.y)), g1 = gelu_erf2(make_float2(a.z, a.w));
-                        a = make_float4(g0.x, g0.y, g1.x, g1.y);
+                    // packed 2 x fp32 math (FFMA2 / FADD2): these epilogues run neck and neck with the MMAs, every issue slot counts
+                    float2 a01 = make_float2(a.x, a.y), a23 = make_float2(a.z, a.w);
+                    const float2 b01 = make_float2(bias4.x, bias4.y), b23 = make_float2(bias4.z, bias4.w);
+                    if (ln_on) {      // LN(x) W^T + b = rstd * (x16 W''^T) + b'   (mean removal lives in the centred weight W'')
+                        const float2 rs2 = make_float2(ln_rs[i], ln_rs[i]);
+                        a01 = ffma2(rs2, a01, b01); a23 = ffma2(rs2, a23, b23);
+                    } else {
+                        a01 = fadd2(a01, b01); a23 = fadd2(a23, b23);
                     }
+                    if (EPI == EPI_GELU16) { a01 = gelu_erf2(a01); a23 = gelu_erf2(a23); }
                     uint2 pk;
-                    pk.x = H::pack(a.x, a.y); pk.y = H::pack(a.z, a.w);
+                    pk.x = H::pack(a01.x, a01.y); pk.y = H::pack(a23.x, a23.y);
                     *reinterpret_cast<uint2*>(static_cast<typename H::T*>(p.out0) + roff[i] + co) = pk;
                 } else if (EPI == EPI_RESID) {
-                    float4 x = pre[i];
-                    x.x += g4.x * (a.x + bias4.x); x.y += g4.y * (a.y + bias4.y);
-                    x.z += g4.z * (a.z + bias4.z); x.w += g4.w * (a.w + bias4.w);
-                    *reinterpret_cast<float4*>(static_cast<float*>(p.out0) + roff[i] + co) = x;
+                    const float2 x01 = ffma2(make_float2(g4.x, g4.y), fadd2(make_float2(a.x, a.y), make_float2(bias4.x, bias4.y)), make_float2(pre[i].x, pre[i].y));
+                    const float2 x23 = ffma2(make_float2(g4.z, g4.w), fadd2(make_float2(a.z, a.w), make_float2(bias4.z, bias4.w)), make_float2(pre[i].z, pre[i].w));
+                    *reinterpret_cast<float4*>(static_cast<float*>(p.out0) + roff[i] + co) = make_float4(x01.x, x01.y, x23.x, x23.y);
+                    if (x16_on) {
+                        uint2 pk;
+                        pk.x = H::pack(x01.x, x01.y); pk.y = H::pack(x23.x, x23.y);
+                        *reinterpret_cast<uint2*>(static_cast<typename H::T*>(p.x16) + roff[i] + co) = pk;
+                        const float2 f0 = H::unpack(pk.x), f1 = H::unpack(pk.y);
+                        const float2 s1 = fadd2(f0, f1), s2 = ffma2(f0, f0, fmul2(f1, f1));
+                        st1[i] += s1.x + s1.y;
+                        st2[i] += s2.x + s2.y;
+                    }
                 } else if (EPI == EPI_PATCH) {
-                    *reinterpret_cast<float4*>(static_cast<float*>(p.out0) + roff[i] + co) =
-                        make_float4(a.x + pre[i].x, a.y + pre[i].y, a.z + pre[i].z, a.w + pre[i].w);
+                    const float4 x = make_float4(a.x + pre[i].x, a.y + pre[i].y, a.z + pre[i].z, a.w + pre[i].w);
+                    *reinterpret_cast<float4*>(static_cast<float*>(p.out0) + roff[i] + co) = x;
+                    if (x16_on) {
+                        uint2 pk;
+                        pk.x = H::pack(x.x, x.y); pk.y = H::pack(x.z, x.w);
+                        *reinterpret_cast<uint2*>(static_cast<typename H::T*>(p.x16) + roff[i] + co) = pk;
+                        const float2 f0 = H::unpack(pk.x), f1 = H::unpack(pk.y);
+                        const float2 s1 = fadd2(f0, f1), s2 = ffma2(f0, f0, fmul2(f1, f1));
+                        st1[i] += s1.x + s1.y;
+                        st2[i] += s2.x + s2.y;
+                    }
                 } else if (EPI == EPI_DEC) {
                     a.x += bias4.x + pre[i].x; a.y += bias4.y + pre[i].y; a.z += bias4.z + pre[i].z; a.w += bias4.w + pre[i].w;
                     if (has_uv) {
@@ -462,6 +515,17 @@ __device__ __forceinline__ void epilogue_tile(const UmmaParams& p, int mt, int n
                     }
             }
             __syncwarp();
+        }
+        // LayerNorm fold, producer side: partial (sum, sum of squares) of this warp's column group for each of its rows
+        if (x16_on) {
+            const int part = (nt * BN + col_begin) / COLS;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                float a = st1[i], b = st2[i];
+#pragma unroll
+                for (int o = 1; o < 8; o <<= 1) { a += __shfl_xor_sync(0xffffffffu, a, o); b += __shfl_xor_sync(0xffffffffu, b, o); }
+                if (q4 == 0 && ok[i]) p.stats_out[static_cast<size_t>(xrow[i]) * p.stats_ld + part] = make_float2(a, b);
+            }
         }
     }
 }
@@ -580,15 +644,22 @@ umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
         const int col_begin = (Cfg::kEpiWarps == 8) ? (ew >> 2) * (BN / 2) : 0;
         float4* scr = reinterpret_cast<float4*>(scratch_base + ew * 1024);
         int it = 0;
+        LnRows lnr{}, lnn{};
+        const bool ln_on = AMODE == AMODE_ROWS && (EPI == EPI_STORE16 || EPI == EPI_GELU16) && p.ln_rstd != nullptr;
+        if (ln_on && static_cast<int>(blockIdx.x) < total_tiles) ln_load(p, static_cast<int>(blockIdx.x) / p.num_n_tiles, quarter, lane, lnn);
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
             const int mt = tile / p.num_n_tiles, nt = tile % p.num_n_tiles;
             const int acc = it & 1;
             const uint32_t aph = (it >> 1) & 1;
+            if (ln_on) {        // rstd of this tile's rows (loaded one iteration ago); then issue the next tile's loads
+                lnr = lnn;
+                const int nxt = tile + static_cast<int>(gridDim.x);
+                if (nxt < total_tiles) ln_load(p, nxt / p.num_n_tiles, quarter, lane, lnn);
+            }
             mbar_wait(&tfull[acc], aph);
             tc_fence_after();
             const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN + col_begin;
-
-            epilogue_tile<BN, Cfg::kColsPerWarp, AMODE, EPI, BF16, DF>(p, mt, nt, t_addr, scr, quarter, lane, col_begin);
+            epilogue_tile<BN, Cfg::kColsPerWarp, AMODE, EPI, BF16, DF>(p, mt, nt, t_addr, scr, quarter, lane, col_begin, ln_on, lnr);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tempty[acc]);

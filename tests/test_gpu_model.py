@@ -89,7 +89,9 @@ def test_forward_and_infer_match_reference_golden(name, golden_dir):
     well_posed = bool((f_p > 0).all()) and bool(((raw["points"][..., 2] + s_p[:, None, None])[valid] > 0).all())
     print("focal/shift engine", f_g.tolist(), s_g.tolist(), "scipy", f_p.tolist(), s_p.tolist(), "well-posed:", well_posed)
     if well_posed:
-        assert torch.allclose(f_g.cpu(), f_p, rtol=1e-4, atol=1e-6) and torch.allclose(s_g.cpu(), s_p, rtol=1e-4, atol=1e-5)
+        # both solvers stop on SciPy's ftol = 1e-3 (relative cost decrease), which pins the optimum to a few 1e-4 relative on
+        # these noise-like maps; the tight (bit-level) solver parity on clean maps is test_gpu_geometry.py's job
+        assert torch.allclose(f_g.cpu(), f_p, rtol=5e-4, atol=1e-6) and torch.allclose(s_g.cpu(), s_p, rtol=5e-4, atol=1e-5)
     # (a') infer() == reference post-processing formulas (oracle port) applied to the engine's forward outputs and the
     #      engine's (focal, shift): same inputs on both sides, so K19 + the plumbing of infer() are compared tightly.
     ref = moge_port.postprocess(raw.get("points"), raw.get("normal"), raw.get("mask"), raw.get("metric_scale"), W / H,
@@ -205,6 +207,30 @@ def test_batch_chunking_is_transparent():
     torch.cuda.synchronize()
     for k in full:
         assert torch.equal(full[k], chunked[k]), k
+
+
+def test_layernorm_fold_path_matches_default(monkeypatch):
+    """MOGE_B200_LNFOLD=1: norm1/norm2 folded into the qkv / fc1 GEMMs (rounded residual rows as the A operand, centred weights,
+    rstd in the epilogue; statistics written by the patch-embed / proj / fc2 epilogues).  Same outputs as the default path
+    (separate LayerNorm kernel) to 16-bit rounding noise."""
+    cfg = model_config("vitb", True)
+    sd = make_state_dict(cfg, 3)
+    img = synthetic_images(2, 112, 140, 77).to(DEV)
+
+    def run():
+        m = MoGeModel(**cfg)
+        m.load_state_dict(sd)
+        m = m.to(DEV).eval()
+        out = m.forward(img, 120)
+        torch.cuda.synchronize()
+        return {k: v.float().cpu() for k, v in out.items()}
+
+    base = run()
+    monkeypatch.setenv("MOGE_B200_LNFOLD", "1")
+    fold = run()
+    for k in base:
+        assert rel_l2(fold[k], base[k]) < 2e-3, (k, rel_l2(fold[k], base[k]))
+    assert any(not torch.equal(fold[k], base[k]) for k in base)      # the switch really selected another path
 
 
 def test_serving_pipeline_matches_direct_infer():

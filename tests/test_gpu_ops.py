@@ -62,6 +62,27 @@ def test_linear_residual_layerscale(M, N, K, dtype):
 
 
 @pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("M,N,K,epi", [(1370, 1152, 384, 0), (300, 3072, 1024, 0), (677, 3072, 768, 1), (2 * 1370, 4096, 1024, 1)])
+def test_linear_with_folded_layernorm(M, N, K, epi, dtype):
+    """norm -> linear (-> GELU) computed as ONE GEMM on the rounded residual rows (LayerNorm folded into weights + epilogue),
+    against LayerNorm + linear in fp32.  The rows get a per-row offset and scale so mean and variance matter."""
+    g = torch.Generator(device="cpu").manual_seed(M + N + K)
+    x = (torch.randn(M, K, generator=g) * (0.5 + 2 * torch.rand(M, 1, generator=g)) + torch.randn(M, 1, generator=g)).to(DEV)
+    lg = (1 + 0.3 * torch.randn(K, generator=g)).to(DEV)
+    lb = (0.2 * torch.randn(K, generator=g)).to(DEV)
+    w = (torch.randn(N, K, generator=g) / K ** 0.5).to(DEV)
+    b = torch.randn(N, generator=g).to(DEV)
+    out = torch.empty(M, N, device=DEV, dtype=dtype)
+    capi.check(_lib().moge_op_linear_ln(x.data_ptr(), lg.data_ptr(), lb.data_ptr(), w.data_ptr(), b.data_ptr(), out.data_ptr(), M, N, K, epi,
+                                        dt(dtype), stream()))
+    torch.cuda.synchronize()
+    ref = F.linear(F.layer_norm(x, (K,), lg, lb, 1e-6), w, b)
+    if epi == 1:
+        ref = F.gelu(ref)
+    assert rel_l2(out, ref) < TOL[dtype]
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
 @pytest.mark.parametrize("D", [384, 768, 1024])
 def test_layernorm(D, dtype):
     rows = 1371
