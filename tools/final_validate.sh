@@ -28,6 +28,7 @@ with open("gpurun_out/${TAG}_launch_list_ncu_summary.txt", "w") as f:
         f.write(f"{k:64s} {n:8d} {us:12.1f} {us / tot * 100:6.1f}%\n")
 print(open("gpurun_out/${TAG}_launch_list_ncu_summary.txt").read()[:1500])
 P
+[ -n "$NOFULL" ] && exit 0
 # full captures of the top kernels (one launch each)
 WHAT=attn timeout 300 ncu --set full --clock-control none --import-source on -k regex:attention_kernel -s 2 -c 1 -f -o gpurun_out/${TAG}_attn python tools/prof_conv.py > /dev/null 2>&1
 WHAT=conv64skip timeout 300 ncu --set full --clock-control none --import-source on -k regex:conv64_kernel -s 1 -c 1 -f -o gpurun_out/${TAG}_conv64 python tools/prof_dec.py > /dev/null 2>&1
