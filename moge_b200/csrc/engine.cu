@@ -105,7 +105,7 @@ struct moge_engine {
     struct Blk {
         void *wqkv, *wproj, *wfc1, *wfc2;
         const float *bqkv, *bproj, *bfc1, *bfc2, *g1, *g2, *ln1g, *ln1b, *ln2g, *ln2b;
-        // LayerNorm folded into the GEMM (MOGE_B200_LNFOLD=1): centred W diag(gamma) in 16 bit, b + W beta
+        // LayerNorm folded into the GEMM (default; MOGE_B200_LNFOLD=0 disables): centred W diag(gamma) in 16 bit, b + W beta
         void *wqkv_ln, *wfc1_ln;
         float *b_qkv_ln, *b_fc1_ln;
     };
@@ -118,7 +118,7 @@ struct moge_engine {
     Plan* last_plan = nullptr;
     bool use_graphs = true;
     bool use_2cta = false;
-    bool ln_fold = false;         // MOGE_B200_LNFOLD=1: LayerNorm folded into qkv / fc1 (default: separate layernorm kernel)
+    bool ln_fold = true;          // LayerNorm folded into qkv / fc1; MOGE_B200_LNFOLD=0: separate layernorm kernel
     cudaStream_t own_stream = nullptr;
     cudaEvent_t ev_in = nullptr, ev_out = nullptr;
 
@@ -867,7 +867,7 @@ int moge_engine_create(const moge_config_t* cfg, int device, moge_engine_t** out
     const char* env2 = getenv("MOGE_B200_2CTA");
     e->use_2cta = !(env2 != nullptr && env2[0] == '0');
     const char* env3 = getenv("MOGE_B200_LNFOLD");
-    e->ln_fold = env3 != nullptr && env3[0] == '1';
+    e->ln_fold = !(env3 != nullptr && env3[0] == '0');
     if (cudaStreamCreateWithFlags(&e->own_stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreateWithFlags(&e->ev_in, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&e->ev_out, cudaEventDisableTiming) != cudaSuccess) {

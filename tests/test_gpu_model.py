@@ -209,10 +209,10 @@ def test_batch_chunking_is_transparent():
         assert torch.equal(full[k], chunked[k]), k
 
 
-def test_layernorm_fold_path_matches_default(monkeypatch):
-    """MOGE_B200_LNFOLD=1: norm1/norm2 folded into the qkv / fc1 GEMMs (rounded residual rows as the A operand, centred weights,
-    rstd in the epilogue; statistics written by the patch-embed / proj / fc2 epilogues).  Same outputs as the default path
-    (separate LayerNorm kernel) to 16-bit rounding noise."""
+def test_layernorm_fold_matches_separate_layernorm(monkeypatch):
+    """Default path: norm1/norm2 folded into the qkv / fc1 GEMMs (rounded residual rows as the A operand, centred weights,
+    rstd in the epilogue; statistics written by the patch-embed / proj / fc2 epilogues).  MOGE_B200_LNFOLD=0 selects the separate
+    LayerNorm kernel; both give the same outputs to 16-bit rounding noise."""
     cfg = model_config("vitb", True)
     sd = make_state_dict(cfg, 3)
     img = synthetic_images(2, 112, 140, 77).to(DEV)
@@ -223,14 +223,17 @@ def test_layernorm_fold_path_matches_default(monkeypatch):
         m = m.to(DEV).eval()
         out = m.forward(img, 120)
         torch.cuda.synchronize()
-        return {k: v.float().cpu() for k, v in out.items()}
+        names = [n for n, _, _ in m.engine_ops()]
+        return {k: v.float().cpu() for k, v in out.items()}, names
 
-    base = run()
-    monkeypatch.setenv("MOGE_B200_LNFOLD", "1")
-    fold = run()
-    for k in base:
-        assert rel_l2(fold[k], base[k]) < 2e-3, (k, rel_l2(fold[k], base[k]))
-    assert any(not torch.equal(fold[k], base[k]) for k in base)      # the switch really selected another path
+    monkeypatch.delenv("MOGE_B200_LNFOLD", raising=False)
+    fold, names_fold = run()
+    monkeypatch.setenv("MOGE_B200_LNFOLD", "0")
+    sep, names_sep = run()
+    assert "ln_rstd" in names_fold and "layernorm" not in names_fold
+    assert "layernorm" in names_sep and "ln_rstd" not in names_sep
+    for k in sep:
+        assert rel_l2(fold[k], sep[k]) < 2e-3, (k, rel_l2(fold[k], sep[k]))
 
 
 def test_serving_pipeline_matches_direct_infer():
