@@ -27,6 +27,9 @@ sys.path.insert(0, ROOT)
 import torch  # noqa: E402
 
 
+METRIC = "images/sec ViT-L 518px fp16 (MoGe-2 infer)"      # BASELINE.json metric, same string on both arms
+
+
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -138,7 +141,7 @@ def run_reference(a):
     ips_w, _ = cpu_port_images_per_s(a.size, a.res, a.tokens, 1, threads) if a.warmup > 0 else (0, 0)
     ips, dt = cpu_port_images_per_s(a.size, a.res, a.tokens, a.steps * per_step, threads)
     line = {
-        "impl": "reference", "metric": "images/sec ViT-L 518px (MoGe-2 infer)", "value": ips, "unit": "images/s", "n_gpus": a.gpus,
+        "impl": "reference", "metric": METRIC, "value": ips, "unit": "images/s", "n_gpus": a.gpus,
         "steps": a.steps, "warmup": min(a.warmup, 1), "ms_per_step": 1000.0 * dt / a.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": workload_name(a, h, w), "sample": "1 image per step on the host cores"},
@@ -334,7 +337,7 @@ def run_engine(a):
 
     images = B * world * a.steps
     line = {
-        "metric": "images/sec ViT-L 518px fp16 (MoGe-2 infer)", "value": images / (ms_dev / 1e3), "unit": "images/s", "n_gpus": world,
+        "metric": METRIC, "value": images / (ms_dev / 1e3), "unit": "images/s", "n_gpus": world,
         "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms_dev / a.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": a.dtype, "data": "synthetic",
         "config": {"workload": workload_name(a, h, w), "images_per_gpu": B, "grid": [h, w],

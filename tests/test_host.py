@@ -101,3 +101,59 @@ def test_synthetic_checkpoint_roundtrip(tmp_path):
     sd = make_state_dict(cfg, 3)
     assert set(m.state_dict()) == set(sd) and all(torch.equal(m.state_dict()[k], sd[k]) for k in sd)
     assert m.num_tokens_range == [1200, 3600] and m.remap_output == "exp"
+
+
+def test_layernorm_fold_algebra():
+    """The identity behind the engine's fused LayerNorm + GEMM (moge_b200/csrc/elementwise.cu, ln_fold_kernel):
+    LN(x) W^T + b == rstd * (x W''^T) + b'  with W'' = rows of (W diag(gamma)) centred, b' = b + W beta  (block.py:90,93)."""
+    g = torch.Generator().manual_seed(5)
+    M, K, N = 37, 96, 24
+    x = (torch.randn(M, K, generator=g, dtype=torch.float64) * 3 + torch.randn(M, 1, generator=g, dtype=torch.float64))
+    gamma = 1 + 0.3 * torch.randn(K, generator=g, dtype=torch.float64)
+    beta = 0.2 * torch.randn(K, generator=g, dtype=torch.float64)
+    W = torch.randn(N, K, generator=g, dtype=torch.float64) / K ** 0.5
+    b = torch.randn(N, generator=g, dtype=torch.float64)
+    ref = torch.nn.functional.linear(torch.nn.functional.layer_norm(x, (K,), gamma, beta, 1e-6), W, b)
+    Wg = W * gamma[None, :]
+    W2 = Wg - Wg.mean(dim=1, keepdim=True)                 # centred rows: (x - mean(x) 1) Wg^T == x W2^T
+    b2 = b + W @ beta
+    s1, s2 = x.sum(1), (x * x).sum(1)                      # what the producing epilogues accumulate per row
+    mean = s1 / K
+    rstd = 1.0 / torch.sqrt(s2 / K - mean * mean + 1e-6)
+    out = rstd[:, None] * (x @ W2.T) + b2[None, :]
+    assert torch.allclose(out, ref, rtol=1e-9, atol=1e-9)
+
+
+def test_serving_pipeline_needs_a_cuda_model():
+    from moge.model.v2 import MoGeModel
+    from moge_b200.serving import InferPipeline
+    m = MoGeModel(**model_config("vits", True))
+    with pytest.raises(RuntimeError, match="CUDA"):
+        InferPipeline(m)
+    with pytest.raises(ValueError):
+        InferPipeline(m, depth=0)
+
+
+def test_committed_bench_lines_follow_the_contract():
+    """profiles/r1_bench_n1.json and r1_bench_reference_arm.json are real bench.py lines: check the keys the driver parses."""
+    import json
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    eng = json.load(open(os.path.join(root, "profiles", "r1_bench_n1.json")))
+    ref = json.load(open(os.path.join(root, "profiles", "r1_bench_reference_arm.json")))
+    for line in (eng, ref):
+        for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
+                  "dtype", "data", "config", "e2e", "cpu_baseline", "gpu_launches"):
+            assert k in line, k
+        assert "workload" in line["config"] and "model" not in line["config"]
+        for k in ("value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"):
+            assert k in line["e2e"], k
+        for k in ("value", "unit", "cores", "kind", "sample"):
+            assert k in line["cpu_baseline"], k
+    assert eng["metric"] == ref["metric"] and eng["unit"] == ref["unit"] and eng["config"]["workload"] == ref["config"]["workload"]
+    assert ref["impl"] == "reference" and ref["e2e"]["h2d_bytes_per_step"] == 0 and ref["gpu_launches"] == 0
+    assert eng["gpu_launches"] > 0 and eng["e2e"]["h2d_bytes_per_step"] > 0 and eng["e2e"]["value"] != eng["value"]
+    r = eng["roofline"]
+    for k in ("bound", "achieved", "peak", "unit", "frac", "traffic"):
+        assert k in r, k
+    assert abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9
+    assert {"sm_mhz", "sm_max_mhz", "reasons"} <= set(eng["clocks"])
