@@ -135,8 +135,6 @@ def run_reference(a):
     threads = host_threads()
     h, w = token_grid(a.res, a.res, a.tokens)
     per_step = 1
-    for _ in range(max(a.warmup - 2, 0) if a.warmup > 2 else 0):
-        pass
     # bounded sample: each step = 1 image; warm-up is capped at one image to keep the run within minutes
     ips_w, _ = cpu_port_images_per_s(a.size, a.res, a.tokens, 1, threads) if a.warmup > 0 else (0, 0)
     ips, dt = cpu_port_images_per_s(a.size, a.res, a.tokens, a.steps * per_step, threads)
