@@ -24,6 +24,8 @@ constexpr int ATT_TILE_BYTES = 128 * 128;   // [128 rows][64 x 16-bit]
 constexpr int ATT_THREADS = 128 + 256;   // warpgroup 0: TMA warp, MMA warp, 2 idle; warpgroups 1,2: softmax
 // smem: Q0,Q1 | K[stages] | V[stages] | barriers
 constexpr int ATT_SMEM = (2 + 2 * ATT_KV_STAGES) * ATT_TILE_BYTES + 1024 + 256;
+static_assert(ATT_SMEM <= kMaxDynSmem, "attention_kernel: Q + K/V ring exceed the shared memory of one CTA");
+static_assert((1 + 4 * ATT_KV_STAGES + 8) * 8 + 4 <= 256, "attention_kernel: barrier block overflows its 256 bytes");
 
 #ifdef MG_ATT_DEBUG
 // wait-time attribution (debug builds only; tools/att_debug.py), summed over CTAs, warp 4 lane 0 / warp 1 lane 0:

@@ -58,6 +58,7 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 #ifndef MG_WATCHDOG_SPINS
 #define MG_WATCHDOG_SPINS (1u << 26)
 #endif
+constexpr int kMaxDynSmem = 232448;       // 227 KB: the opt-in dynamic shared memory limit of one CTA on sm_100
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     uint32_t spins = 0;
     while (!mbar_try_wait(bar, parity)) {

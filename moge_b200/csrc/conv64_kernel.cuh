@@ -39,6 +39,9 @@ template <int BN> struct Conv64Cfg {
     static constexpr int kScratchBytes = kEpiWarps * 4096;
     static constexpr int kSmemBytes = kStages * kABytes + kWBytes + 1024 + 256 + kScratchBytes;
     static constexpr int kColsPerWarp = BN;
+    static_assert(kSmemBytes <= kMaxDynSmem, "conv64_kernel: halo ring + resident weights + scratch exceed the shared memory of one CTA");
+    static_assert((2 * kStages + 2 * kAccStages + 1) * 8 + 4 <= 256, "conv64_kernel: barrier block overflows its 256 bytes");
+    static_assert(kAccStages * BN <= 512, "conv64_kernel: accumulator stages exceed tensor memory");
 };
 
 template <int BN, int EPI, bool BF16, int DF>

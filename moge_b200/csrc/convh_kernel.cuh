@@ -26,6 +26,8 @@ template <int BN> struct ConvhCfg {
     static constexpr int kScratchBytes = kEpiWarps * 4096;
     static constexpr int kSmemBytes = kAStages * kABytes + kWStages * kWBytes + 1024 + 256 + kScratchBytes;
     static constexpr int kColsPerWarp = BN / 2;
+    static_assert(kSmemBytes <= kMaxDynSmem, "convh_kernel: box ring + weight ring + scratch exceed the shared memory of one CTA");
+    static_assert((2 * kAStages + 2 * kWStages + 4) * 8 + 4 <= 256, "convh_kernel: barrier block overflows its 256 bytes");
 };
 
 template <int BN, bool BF16, int DF>

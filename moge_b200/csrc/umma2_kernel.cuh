@@ -63,6 +63,8 @@ struct Umma2Cfg {
     static constexpr int kTmemCols = 512;
     static constexpr int kScratchBytes = kEpiWarps * 4096;
     static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256 + kScratchBytes;
+    static_assert(kSmemBytes <= kMaxDynSmem, "umma2_kernel: stage ring + scratch exceed the shared memory of one CTA");
+    static_assert((2 * kStages + 4) * 8 + 4 <= 256, "umma2_kernel: barrier block overflows its 256 bytes");
 };
 
 template <int EPI, bool BF16>

@@ -74,6 +74,8 @@ template <int BN> struct UmmaCfg {
     static constexpr int kScratchBytes = kEpiWarps * 4096;   // per-epilogue-warp 32x32 fp32 transpose tile
     static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/ + kScratchBytes;
     static constexpr int kColsPerWarp = (kEpiWarps == 8) ? BN / 2 : BN;
+    static_assert(kSmemBytes <= kMaxDynSmem, "umma_kernel: stage ring + scratch exceed the shared memory of one CTA");
+    static_assert((2 * kStages + 4) * 8 + 4 <= 256, "umma_kernel: barrier block overflows its 256 bytes");
 };
 
 // Exact-erf GELU (nn.GELU() default, vision_transformer.py:61): gelu(x) = relu(x) - 0.5 |x| erfc(|x|/sqrt2), with
