@@ -44,6 +44,10 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-images", type=int, default=2)
     ap.add_argument("--dump-ops", default=None, help="write the per-launch profile (name, ms, flops, bytes) to this JSON file")
+    ap.add_argument("--config", type=int, default=0, help="0: the driver's default line (BASELINE.json configs[1]/[3]); 3: mixed-aspect "
+                    "~700-token ViT-L-normal bf16 batch (configs[2]); 5: ViT-B resolution / aspect sweep (configs[4])")
+    ap.add_argument("--no-gpu-baseline", action="store_true", help="skip the same-box PyTorch-CUDA comparator (gpu_baseline)")
+    ap.add_argument("--gpu-baseline-kernels", default=None, help="write the torch.profiler kernel list of one batch-1 comparator pass here")
     return ap.parse_args()
 
 
@@ -120,6 +124,71 @@ def cpu_port_images_per_s(size, res, tokens, n_images, threads):
         moge_port.infer(cfg, sd, img, num_tokens=tokens)
     dt = time.perf_counter() - t0
     return n_images / dt, dt
+
+
+def gpu_baseline(cfg, sd, dev, res, tokens, batch, iters_b1=200, kernels_path=None):
+    """Same-box PyTorch-CUDA comparator (SURVEY.md 8d "Reference GPU baseline"): the reference's algorithm as plain PyTorch ops
+    (oracle/moge_port.py -> cuBLAS / cuDNN / SDPA kernels, SciPy focal solve on the host exactly like geometry_torch.py:150-166),
+    in the reference's two 16-bit modes: (i) `.half()` weights + input, (ii) fp32 weights under torch.autocast(fp16)
+    (v2.py:241).  Batch-1 latency (p50 / p90 over `iters_b1` runs, CUDA events, host solve inside) and batch-`batch` images/s."""
+    import contextlib
+    from oracle import moge_port
+    out = {"kind": "oracle port (the reference's algorithm as plain PyTorch ops) on cuda: cuBLAS/cuDNN/SDPA + host SciPy solve",
+           "torch": torch.__version__}
+    g = torch.Generator().manual_seed(99)
+    img = torch.rand(batch, 3, res, res, generator=g).to(dev)
+    aspect = 1.0
+    for mode in ("half", "autocast"):
+        if mode == "half":
+            sdd = {k: v.to(dev).half() for k, v in sd.items() if v.is_floating_point()}
+            x_all, ctx = img.half(), contextlib.nullcontext
+        else:
+            sdd = {k: v.to(dev).float() for k, v in sd.items() if v.is_floating_point()}
+            x_all, ctx = img, (lambda: torch.autocast("cuda", dtype=torch.float16))
+
+        def run(x):
+            with torch.inference_mode():
+                with ctx():
+                    raw = moge_port.forward(cfg, sdd, x, tokens)
+                raw = {k: v.float() for k, v in raw.items()}
+                return moge_port.postprocess(raw.get("points"), raw.get("normal"), raw.get("mask"), raw.get("metric_scale"), aspect)
+
+        one = x_all[:1].contiguous()
+        for _ in range(10):
+            run(one)
+        torch.cuda.synchronize()
+        lat = []
+        for _ in range(iters_b1):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            run(one)
+            e1.record()
+            torch.cuda.synchronize()
+            lat.append(e0.elapsed_time(e1))
+        run(x_all)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        nrep = 3
+        for _ in range(nrep):
+            run(x_all)
+        e1.record()
+        torch.cuda.synchronize()
+        out[mode] = {"batch1_p50_ms": statistics.median(lat), "batch1_p90_ms": sorted(lat)[int(0.9 * len(lat))], "batch1_iters": len(lat),
+                     "batch": batch, "images_per_s": batch * nrep / (e0.elapsed_time(e1) / 1e3)}
+        if kernels_path and mode == "half":
+            from torch.profiler import profile, ProfilerActivity
+            with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
+                run(one)
+                torch.cuda.synchronize()
+            rows = [{"kernel": e.key, "calls": e.count, "cuda_us": e.device_time_total} for e in prof.key_averages()
+                    if getattr(e, "device_time_total", 0) > 0 and e.device_type.name == "CUDA"]
+            rows.sort(key=lambda r: -r["cuda_us"])
+            with open(kernels_path, "w") as fh:
+                json.dump({"mode": mode, "batch": 1, "launches": sum(r["calls"] for r in rows),
+                           "cuda_us_total": sum(r["cuda_us"] for r in rows), "kernels": rows[:60]}, fh, indent=1)
+        del sdd
+    return out
 
 
 def workload_name(a, h, w):
@@ -251,14 +320,30 @@ def run_engine(a):
     pipe.join()
     ms_e2e = timed(step_pipe, a.steps, fence=pipe.fence)
 
-    # ---- output gather to rank 0 over NCCL (config 4 of BASELINE.json), measured separately
+    # ---- BASELINE.json configs[3] as defined: "inputs resident on each GPU -> all outputs resident on rank 0".  Every step ends
+    #      with a gather of the five output maps to rank 0 over NCCL (one grouped isend/irecv batch into preallocated full-batch
+    #      buffers, parallel.OutputGatherer) on a side stream, so the transfer of step i runs under the compute of step i+1; the
+    #      timed region ends when the LAST step's outputs are on rank 0.  At N > 1 this is the line's `value`.
     gather = None
+    ms_gather = None
     if world > 1:
-        o = model.infer(dev_in, num_tokens=a.tokens)
-        counts = [B] * world
-        parallel.gather_outputs(o, counts)                     # first call sets up the P2P channels
-        ms_g = timed(lambda: parallel.gather_outputs(o, counts), 1)
-        gather = {"ms": ms_g, "bytes_to_rank0": d2h_bytes * (world - 1)}
+        gat = parallel.OutputGatherer([B] * world, device=dev)
+
+        def step_gather():
+            gat.submit(model.infer(dev_in, num_tokens=a.tokens))
+
+        def step_gather_serial():
+            gat.submit(model.infer(dev_in, num_tokens=a.tokens))
+            gat.fence()
+
+        for _ in range(2):
+            step_gather()                                       # first calls set up the P2P channels / buffers
+        gat.wait()
+        ms_gather = timed(step_gather, a.steps, fence=gat.fence)
+        ms_gather_serial = timed(step_gather_serial, a.steps, fence=gat.fence)
+        gather = {"bytes_to_rank0_per_step": d2h_bytes * (world - 1), "ms_per_step_pipelined": ms_gather / a.steps,
+                  "ms_per_step_serial": ms_gather_serial / a.steps, "ms_per_step_no_gather": ms_dev / a.steps,
+                  "api": "moge_b200.parallel.OutputGatherer.submit(infer(...)) per step, fence() at the end"}
 
     if rank != 0:
         if world > 1:
@@ -300,8 +385,13 @@ def run_engine(a):
                 "share_of_step": t * 1e3 / total_prof_ms, "peak_source": pk["source"]}
     idx, t, fl, by = cls(("conv",))
     dec_bound_s = max(fl / (pk["tflops"] * 1e12), by / (pk["hbm_gbs"] * 1e9))
-    roofline_decoder = {"kernel": "umma_kernel<AMODE_TILES> + conv64_kernel (implicit-GEMM convs)", "bound": "hbm",
-                        "achieved": by / t / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": by / t / 1e9 / pk["hbm_gbs"],
+    # algorithmic bytes: SURVEY.md 8(d) "every tensor that crosses a conv boundary once": 501 760 elements x T per image at 2 bytes
+    # (the engine's own per-launch count `by` is LOWER -- its load-time folds removed tensors -- and is reported beside it)
+    by_survey = 501760.0 * (h * w) * 2 * B
+    roofline_decoder = {"kernel": "umma_kernel<AMODE_TILES> + convh_kernel + conv64_kernel (implicit-GEMM convs)", "bound": "hbm",
+                        "achieved": by_survey / t / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": by_survey / t / 1e9 / pk["hbm_gbs"],
+                        "bytes_definition": "SURVEY.md 8(d): 501760 * T elements * 2 B per image (conv-boundary tensors once)",
+                        "engine_bytes_per_step": by, "frac_engine_bytes": by / t / 1e9 / pk["hbm_gbs"],
                         "tensor_tflops": fl / t / 1e12, "frac_of_max_bound": dec_bound_s / t, "traffic": traffic_of("decoder")[0],
                         "traffic_detail": traffic_of("decoder")[1], "launches": len(idx),
                         "ms_per_step": t * 1e3, "share_of_step": t * 1e3 / total_prof_ms}
@@ -333,10 +423,15 @@ def run_engine(a):
         cpu = {"value": ips, "unit": "images/s", "cores": threads, "kind": "port",
                "sample": f"{a.cpu_images} single-image infer() calls ({dt:.1f} s), oracle/moge_port.py fp32, torch CPU {threads} threads"}
 
+    gpu_base = None
+    if world == 1 and not a.no_gpu_baseline:
+        gpu_base = gpu_baseline(cfg, make_state_dict(cfg, 0), dev, R, a.tokens, B, kernels_path=a.gpu_baseline_kernels)
+
     images = B * world * a.steps
+    ms_value = ms_gather if ms_gather is not None else ms_dev       # N > 1: the gather to rank 0 is inside the timed region
     line = {
-        "metric": METRIC, "value": images / (ms_dev / 1e3), "unit": "images/s", "n_gpus": world,
-        "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms_dev / a.steps, "higher_is_better": True, "scaling": "weak",
+        "metric": METRIC, "value": images / (ms_value / 1e3), "unit": "images/s", "n_gpus": world,
+        "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms_value / a.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": a.dtype, "data": "synthetic",
         "config": {"workload": workload_name(a, h, w), "images_per_gpu": B, "grid": [h, w],
                    "l2": "per-step working set (activation workspace, GBs) far exceeds the 126 MB L2; no explicit flush",
@@ -353,10 +448,15 @@ def run_engine(a):
         "profile_ms": {"sum_of_launches": total_prof_ms, "other_kernels": other_ms},
         "latency": latency,
         "cpu_baseline": cpu,
+        "gpu_baseline": gpu_base,
         "load_s": load_s,
     }
+    line["value_compute_only"] = images / (ms_dev / 1e3)
     if gather:
         line["gather"] = gather
+        line["value_with_gather"] = line["value"]
+        line["config"]["value_definition"] = ("N > 1: images/s from inputs resident on each GPU to ALL outputs resident on rank 0 "
+                                              "(NCCL gather inside the timed region, overlapped with the next step's compute)")
     sys.stdout.flush()
     os.dup2(saved_stdout, 1)
     print(json.dumps(line), flush=True)
@@ -364,9 +464,175 @@ def run_engine(a):
         dist.destroy_process_group()
 
 
+def _class_times(model, ops_prefixes=("gemm.", "attention", "conv")):
+    """One CUDA-event replay of the last forward's launch list -> {class: (seconds, flops, bytes)} (best of 3)."""
+    ops = model.engine_ops()
+    prof = [model.engine_profile() for _ in range(3)]
+    ms = [min(p[i] for p in prof) for i in range(len(ops))]
+    out = {}
+    for pre in ops_prefixes:
+        idx = [i for i, (n, _, _) in enumerate(ops) if n.startswith(pre)]
+        out[pre] = (sum(ms[i] for i in idx) / 1e3, sum(ops[i][1] for i in idx), sum(ops[i][2] for i in idx))
+    out["all"] = (sum(ms) / 1e3, sum(o[1] for o in ops), sum(o[2] for o in ops))
+    return out
+
+
+def _timed_steps(fn, steps, warmup):
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / steps
+
+
+def decoder_bytes_survey(c0, tokens, images):
+    """conv-boundary tensors once, 2-byte storage: neck 3E0+14E1+14E2+14E3+E4, each head 3E0+12E1+12E2+12E3+5E4."""
+    e = [c0, 1024, 2048, 4096, 8192]
+    neck = 3 * e[0] + 14 * (e[1] + e[2] + e[3]) + e[4]
+    head = 3 * e[0] + 12 * (e[1] + e[2] + e[3]) + 5 * e[4]
+    return (neck + 3 * head) * 2.0 * tokens * images
+
+
+def run_config3(a):
+    """BASELINE.json configs[2]: ViT-L-normal bf16, 32 images of ~700 tokens in five aspect ratios on ONE B200 -- encoder tensor-pipe
+    roofline.  (a) the reference's only option, same-shape sub-batches (five infer() calls); (b) ragged packing, ONE engine call
+    (infer_many): every linear over the concatenated token rows, attention over a ragged work list."""
+    from moge.model.v2 import MoGeModel
+    from moge_b200.configs import model_config, token_grid
+    from moge_b200.synthetic import make_state_dict
+    dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+    torch.cuda.set_device(dev)
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
+    cfg = model_config("vitl", True)
+    model = MoGeModel(**cfg)
+    model.load_state_dict(make_state_dict(cfg, 0))
+    model = model.to(dev).eval().bfloat16()
+    shapes = [(518, 1036, 7), (518, 777, 7), (518, 518, 6), (777, 518, 6), (1036, 518, 6)]      # (H, W, count): grids 19x37 22x32 26x26 32x22 37x19
+    tokens = 700
+    g = torch.Generator().manual_seed(7)
+    batches = [torch.rand(n, 3, H, W, generator=g).to(dev) for (H, W, n) in shapes]
+    images = [im for b in batches for im in b]
+    grids = [token_grid(H, W, tokens) for (H, W, _) in shapes]
+    nimg = len(images)
+
+    def step_bucketed():
+        for b in batches:
+            model.infer(b, num_tokens=tokens)
+
+    def step_ragged():
+        model.infer_many(images, num_tokens=tokens)
+
+    ms_b = _timed_steps(step_bucketed, a.steps, a.warmup)
+    ms_r = _timed_steps(step_ragged, a.steps, a.warmup)
+    step_ragged()
+    cls = _class_times(model)
+    pk = peaks()
+    enc_t = cls["gemm."][0] + cls["attention"][0]
+    enc_f = cls["gemm."][1] + cls["attention"][1]
+    # bucketed: sum the classes over the five calls
+    enc_tb = enc_fb = 0.0
+    for b in batches:
+        model.infer(b, num_tokens=tokens)
+        c = _class_times(model)
+        enc_tb += c["gemm."][0] + c["attention"][0]
+        enc_fb += c["gemm."][1] + c["attention"][1]
+    line = {
+        "metric": "images/sec ViT-L-normal bf16, 32 mixed-aspect ~700-token images (BASELINE.json configs[2])", "value": nimg / (ms_r / 1e3),
+        "unit": "images/s", "n_gpus": 1, "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms_r, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": "MoGe-2 vitl (normal head) bf16 infer(), 32 images: " + ", ".join(f"{n} x {W}x{H} -> {gh}x{gw}" for (H, W, n), (gh, gw) in zip(shapes, grids))
+                               + f" (W x H -> h x w grid), num_tokens={tokens}", "images": nimg},
+        "ragged": {"api": "model.infer_many(list of 32 images): ONE engine call, 5 shape groups", "images_per_s": nimg / (ms_r / 1e3), "ms_per_step": ms_r,
+                   "encoder": {"tflops": enc_f / enc_t / 1e12, "frac_of_tensor_peak": enc_f / enc_t / 1e12 / pk["tflops"], "ms": enc_t * 1e3,
+                               "gemm_tflops": cls["gemm."][1] / cls["gemm."][0] / 1e12, "attention_tflops": cls["attention"][1] / cls["attention"][0] / 1e12}},
+        "bucketed": {"api": "five model.infer(same-shape sub-batch) calls (what the reference's API allows)", "images_per_s": nimg / (ms_b / 1e3), "ms_per_step": ms_b,
+                     "encoder": {"tflops": enc_fb / enc_tb / 1e12, "frac_of_tensor_peak": enc_fb / enc_tb / 1e12 / pk["tflops"], "ms": enc_tb * 1e3}},
+        "roofline": {"bound": "tensor", "achieved": enc_f / enc_t / 1e12, "peak": pk["tflops"], "unit": "TFLOP/s", "frac": enc_f / enc_t / 1e12 / pk["tflops"],
+                     "kernel": "encoder (linears + attention) of the ragged call", "traffic": None, "peak_source": pk["source"]},
+    }
+    sys.stdout.flush()
+    os.dup2(saved_stdout, 1)
+    print(json.dumps(line), flush=True)
+
+
+def run_config5(a):
+    """BASELINE.json configs[4]: ViT-B, batch 8 per GPU, long side {256..1024} x aspect {2:1..1:2} x resolution_level {0,5,9}: the
+    variable-token encoder + the decoder's HBM roofline.  One row per (H x W, level): (model, dtype, B, HxW, T_req -> h x w), images/s,
+    decoder ms and its fraction of the HBM bound by SURVEY.md 8(d)'s byte count."""
+    from moge.model.v2 import MoGeModel
+    from moge_b200.configs import model_config, token_grid, default_num_tokens
+    from moge_b200.synthetic import make_state_dict
+    dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+    torch.cuda.set_device(dev)
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
+    cfg = model_config("vitb", True)
+    model = MoGeModel(**cfg)
+    model.load_state_dict(make_state_dict(cfg, 0))
+    model = model.to(dev).eval()
+    if a.dtype == "bf16":
+        model = model.bfloat16()
+    pk = peaks()
+    B = 8
+    rows = []
+    g = torch.Generator().manual_seed(11)
+    for long_side in (256, 384, 518, 768, 1024):
+        for (aw, ah) in ((2, 1), (3, 2), (1, 1), (2, 3), (1, 2)):
+            if aw >= ah:
+                W, H = long_side, int(round(long_side * ah / aw))
+            else:
+                H, W = long_side, int(round(long_side * aw / ah))
+            x = torch.rand(B, 3, H, W, generator=g).to(dev)
+            for level in (0, 5, 9):
+                treq = default_num_tokens(cfg["num_tokens_range"], level)
+                h, w = token_grid(H, W, treq)
+                ms = _timed_steps(lambda: model.infer(x, resolution_level=level), max(2, a.steps // 2), 1)
+                c = _class_times(model)
+                t_dec, f_dec, b_dec = c["conv"]
+                bs = decoder_bytes_survey(768, h * w, B)
+                enc_t = c["gemm."][0] + c["attention"][0]
+                enc_f = c["gemm."][1] + c["attention"][1]
+                rows.append({"model": "vitb", "dtype": a.dtype, "B": B, "HxW": [H, W], "T_req": treq, "grid": [h, w], "images_per_s": B / (ms / 1e3),
+                             "ms_per_step": ms, "decoder_ms": t_dec * 1e3, "decoder_gbs_survey_bytes": bs / t_dec / 1e9,
+                             "decoder_frac_hbm": bs / t_dec / 1e9 / pk["hbm_gbs"], "decoder_tflops": f_dec / t_dec / 1e12,
+                             "decoder_frac_of_max_bound": max(f_dec / (pk["tflops"] * 1e12), bs / (pk["hbm_gbs"] * 1e9)) / t_dec,
+                             "encoder_tflops": enc_f / enc_t / 1e12, "encoder_frac": enc_f / enc_t / 1e12 / pk["tflops"]})
+            del x
+    tot_img = sum(r["B"] for r in rows)
+    tot_s = sum(r["ms_per_step"] for r in rows) / 1e3
+    dec_t = sum(r["decoder_ms"] for r in rows) / 1e3
+    dec_b = sum(decoder_bytes_survey(768, r["grid"][0] * r["grid"][1], r["B"]) for r in rows)
+    line = {
+        "metric": "images/sec ViT-B resolution/aspect sweep, batch 8 (BASELINE.json configs[4])", "value": tot_img / tot_s, "unit": "images/s", "n_gpus": 1,
+        "steps": max(2, a.steps // 2), "warmup": 1, "ms_per_step": 1e3 * tot_s / len(rows), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": a.dtype, "data": "synthetic",
+        "config": {"workload": "MoGe-2 vitb* (SURVEY.md 8 test config) infer(), B=8, long side {256,384,518,768,1024} x aspect {2:1,3:2,1:1,2:3,1:2} x "
+                               "resolution_level {0,5,9}; value = total images / total time over the 75 rows", "rows": len(rows)},
+        "roofline": {"bound": "hbm", "achieved": dec_b / dec_t / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": dec_b / dec_t / 1e9 / pk["hbm_gbs"],
+                     "kernel": "decoder conv launches over the whole sweep", "bytes_definition": "SURVEY.md 8(d), 997376 B x T per image", "traffic": None,
+                     "peak_source": pk["source"]},
+        "rows": rows,
+    }
+    sys.stdout.flush()
+    os.dup2(saved_stdout, 1)
+    print(json.dumps(line), flush=True)
+
+
 if __name__ == "__main__":
     args = parse()
     if args.impl == "reference":
         run_reference(args)
+    elif args.config == 3:
+        run_config3(args)
+    elif args.config == 5:
+        run_config5(args)
     else:
         run_engine(args)

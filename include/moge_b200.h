@@ -10,7 +10,8 @@
  *   - no C++ exceptions cross the ABI; no torch types; plain device pointers + sizes.
  *   - all work is enqueued on the `stream` argument (a cudaStream_t passed as void*); nothing synchronises the device.
  *   - the caller owns every input/output tensor and the workspace; the engine owns its packed weights.
- *   - one engine per device; calls on one engine must be serialised by the caller (stream order).
+ *   - calls on one engine must be serialised by the caller (stream order); engines on different devices (or several engines
+ *     on one device) may live in one process and be driven from different threads.
  *   - there is NO CPU fallback: without a sm_100 device every compute entry point fails.
  */
 #ifndef MOGE_B200_H
@@ -85,6 +86,23 @@ int moge_engine_workspace_bytes(moge_engine_t* e, int B, int H, int W, int h, in
 int moge_engine_forward(moge_engine_t* e, const void* image, int image_dtype, int B, int H, int W, int h, int w,
                         void* workspace, size_t workspace_bytes, float* points, float* normal, float* mask_prob,
                         float* metric_scale, void* stream);
+
+/* Mixed-shape ("ragged") batches -- BASELINE.json configs[2]; the reference has no counterpart (a batch tensor has one shape and
+ * its nested-tensor path, dinov2/layers/block.py:160-259, is dead code without xformers).  A call carries `n` shape groups; the
+ * encoder (every linear, the attention) runs ONCE over the token rows of all groups packed back to back, the per-pixel stages
+ * (resize/patchify, pos embed, decoder, output resize) run group by group.  moge_engine_forward is the n = 1 case. */
+typedef struct moge_group {
+    const void* image;          /* (B,3,H,W) in [0,1] */
+    int image_dtype;            /* MOGE_F32 / MOGE_F16 / MOGE_BF16 */
+    int B, H, W, h, w;          /* images, pixels, token grid of this group */
+    float* points;              /* (B,H,W,3) or NULL */
+    float* normal;              /* (B,H,W,3) or NULL */
+    float* mask_prob;           /* (B,H,W) or NULL */
+    float* metric_scale;        /* (B,) or NULL */
+} moge_group_t;
+int moge_engine_workspace_bytes_groups(moge_engine_t* e, const moge_group_t* groups, int n, size_t* bytes);
+int moge_engine_forward_groups(moge_engine_t* e, const moge_group_t* groups, int n, void* workspace, size_t workspace_bytes,
+                               void* stream);
 
 /* ---- introspection of the launch list of the most recent forward (used by bench.py for the roofline numbers):
  * number of kernel launches, per-launch kernel class / algorithmic flops / algorithmic HBM bytes, and a profiling

@@ -19,7 +19,8 @@ RESAMPLE = {"conv_transpose": 0, "bilinear": 1}
 
 EXPORTS = [
     "moge_last_error", "moge_version", "moge_engine_create", "moge_engine_destroy", "moge_engine_set_weight",
-    "moge_engine_finalize", "moge_engine_workspace_bytes", "moge_engine_forward", "moge_engine_num_ops", "moge_engine_op_info", "moge_engine_profile", "moge_recover_focal_shift",
+    "moge_engine_finalize", "moge_engine_workspace_bytes", "moge_engine_forward", "moge_engine_workspace_bytes_groups",
+    "moge_engine_forward_groups", "moge_engine_num_ops", "moge_engine_op_info", "moge_engine_profile", "moge_recover_focal_shift",
     "moge_postprocess", "moge_op_linear", "moge_op_linear_ln", "moge_op_attention", "moge_op_layernorm", "moge_op_conv",
 ]
 
@@ -40,6 +41,15 @@ class Config(C.Structure):
         ("neck", StackConfig), ("points_head", StackConfig), ("normal_head", StackConfig), ("mask_head", StackConfig),
         ("scale_head_layers", C.c_int), ("scale_head_dims", C.c_int * MOGE_MAX_MLP),
         ("remap_output", C.c_int), ("compute_dtype", C.c_int),
+    ]
+
+
+class Group(C.Structure):
+    """moge_group_t: one shape group of a mixed-shape forward call."""
+    _fields_ = [
+        ("image", C.c_void_p), ("image_dtype", C.c_int),
+        ("B", C.c_int), ("H", C.c_int), ("W", C.c_int), ("h", C.c_int), ("w", C.c_int),
+        ("points", C.c_void_p), ("normal", C.c_void_p), ("mask_prob", C.c_void_p), ("metric_scale", C.c_void_p),
     ]
 
 
@@ -69,6 +79,8 @@ def lib() -> C.CDLL:
     L.moge_engine_finalize.argtypes = [vp, vp]
     L.moge_engine_workspace_bytes.argtypes = [vp, ci, ci, ci, ci, ci, C.POINTER(C.c_size_t)]
     L.moge_engine_forward.argtypes = [vp, vp, ci, ci, ci, ci, ci, ci, vp, C.c_size_t, cf, cf, cf, cf, vp]
+    L.moge_engine_workspace_bytes_groups.argtypes = [vp, C.POINTER(Group), ci, C.POINTER(C.c_size_t)]
+    L.moge_engine_forward_groups.argtypes = [vp, C.POINTER(Group), ci, vp, C.c_size_t, vp]
     L.moge_engine_num_ops.argtypes = [vp, C.POINTER(ci)]
     L.moge_engine_op_info.argtypes = [vp, ci, C.c_char_p, ci, C.POINTER(C.c_double), C.POINTER(C.c_double)]
     L.moge_engine_profile.argtypes = [vp, C.POINTER(C.c_float), ci, vp]

@@ -8,11 +8,7 @@ template <int BN, int EPI, bool BF16, int DF>
 static int launch_inst(const CUtensorMap& a, const CUtensorMap& aux, const CUtensorMap& w, const UmmaParams& p, int num_sms, cudaStream_t st) {
     using Cfg = Conv64Cfg<BN>;
     auto kern = conv64_kernel<BN, EPI, BF16, DF>;
-    static bool attr_set = false;
-    if (!attr_set) {
-        CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
-        attr_set = true;
-    }
+    MG_SET_SMEM_ONCE(kern, Cfg::kSmemBytes);
     const int nnt = p.num_n_tiles;
     int grid = (num_sms / nnt) * nnt;
     if (p.num_m_tiles * nnt < grid) grid = p.num_m_tiles * nnt;
@@ -42,6 +38,7 @@ int launch_conv64(int bn, int epi, bool bf16, const CUtensorMap& a, const CUtens
     df = -1;
     INST(64, EPI_DEC, -1)
     INST(16, EPI_HEADOUT, -1)
+    INST(32, EPI_NECKOUT, -1)
 #undef INST
     return set_error("no conv64 instantiation for bn=%d epi=%d", bn, epi);
 }

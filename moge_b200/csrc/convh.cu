@@ -8,11 +8,7 @@ template <int BN, bool BF16, int DF>
 static int launch_inst(const CUtensorMap& a, const CUtensorMap& aux, const CUtensorMap& w, const UmmaParams& p, int num_sms, cudaStream_t st) {
     using Cfg = ConvhCfg<BN>;
     auto kern = convh_kernel<BN, BF16, DF>;
-    static bool attr_set = false;
-    if (!attr_set) {
-        CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
-        attr_set = true;
-    }
+    MG_SET_SMEM_ONCE(kern, Cfg::kSmemBytes);
     const int tiles = p.num_m_tiles * p.num_n_tiles;
     if (tiles <= 0) return 0;
     const int grid = tiles < num_sms ? tiles : num_sms;

@@ -54,8 +54,10 @@ struct StackW {
     std::vector<ConvW> post;                    // [level] 3x3 after the resampler (writes level l+1), fused in-block / UV
     // folded last level of a head
     ConvW headout;
-    float* waux = nullptr;
+    float* waux = nullptr;          // [ncomp, 32] = output block o last-level input block (applied to the neck's last-level map)
     int ncomp = 0;
+    // neck only: its last level folded through the heads' waux (EPI_NECKOUT): N = 4 phases x 8 components
+    ConvW neckout;
 };
 
 struct Op {
@@ -63,31 +65,53 @@ struct Op {
     std::string name;      // kernel class + role, e.g. "gemm.qkv", "conv3x3.neck.l2", "attention"
     double flops = 0;      // algorithmic flops (2*MAC) of this launch
     double bytes = 0;      // algorithmic HBM bytes of this launch (each operand/result once)
+    int phase = 1;         // 0: reads a caller-bound input (preprocess)   1: touches the workspace only (graph-capturable with a
+                           // key that is just the workspace)   2: writes a caller-bound output (scale head, head output)
 };
 
 struct OpList : std::vector<Op> {
-    void add(std::function<int(cudaStream_t)> fn, const char* name, double flops = 0, double bytes = 0) {
-        Op o; o.fn = std::move(fn); o.name = name; o.flops = flops; o.bytes = bytes;
+    void add(std::function<int(cudaStream_t)> fn, const std::string& name, double flops = 0, double bytes = 0, int phase = 1) {
+        Op o; o.fn = std::move(fn); o.name = name; o.flops = flops; o.bytes = bytes; o.phase = phase;
         push_back(std::move(o));
     }
 };
 
-struct Plan {
-    int B, H, W, h, w;
-    void* ws;
-    size_t ws_bytes;
-    OpList ops;
-    float* pos_table = nullptr;   // engine-owned, [T, D]
-    float* cls_row = nullptr;
-    bool table_ready = false;
-    // output bindings (set per forward)
-    float* points = nullptr; float* normal = nullptr; float* mask = nullptr; float* scale = nullptr;
+// One shape group of a forward call: B images of H x W pixels on an h x w token grid.  A call may carry several groups
+// (mixed-aspect batches): the encoder runs ONCE over the token rows of all groups packed back to back, everything that
+// depends on the pixel geometry (preprocess, patch/pos embed, taps, decoder, output resize) runs per group.
+struct Group {
+    int B = 0, H = 0, W = 0, h = 0, w = 0;
+    int img0 = 0;                 // index of the group's first image among all images of the call
+    long row0 = 0;                // first row of the group in the packed token matrices
+    float* pos_table = nullptr;   // plan-owned, [h*w, D] (bicubic-resampled pos embed + patch bias)
+    // bindings (set per forward)
     const void* image = nullptr; int image_dtype = 0;
-    // CUDA graphs of the launch list, one per distinct binding of the caller's pointers (the launch list of a
-    // single image is ~240 kernels of a few microseconds each: replaying a graph removes the per-launch CPU cost)
-    struct GraphEntry { const void* key[6]; int dtype; cudaGraphExec_t exec; };
-    std::vector<GraphEntry> graphs;
+    float* points = nullptr; float* normal = nullptr; float* mask = nullptr; float* scale = nullptr;
+};
+
+struct Plan {
+    std::vector<Group> groups;
+    void* ws = nullptr;
+    size_t ws_bytes = 0;
+    OpList ops;                    // in launch order: all phase-0 ops, then phase 1, then phase 2
+    std::vector<void*> owned;      // device buffers that live and die with the plan (pos tables, cls row, attention work list)
+    float* cls_row = nullptr;
+    std::vector<AttnItem> att_items; std::vector<int2> att_ranges;     // host copies (source of the async upload)
+    // ONE CUDA graph of the phase-1 launches (they touch nothing but the workspace the plan is keyed on, so the graph never
+    // goes stale when the caller passes fresh input / output tensors): the launch list of a single image is ~240 kernels of a
+    // few microseconds each and replaying a graph removes the per-launch CPU cost.  Phase 0 / 2 launches run eagerly around it.
+    cudaGraphExec_t exec = nullptr;
     int eager_runs = 0;
+    bool same_shape(const moge_group_t* g, int n) const {
+        if (static_cast<int>(groups.size()) != n) return false;
+        for (int i = 0; i < n; ++i)
+            if (groups[i].B != g[i].B || groups[i].H != g[i].H || groups[i].W != g[i].W || groups[i].h != g[i].h || groups[i].w != g[i].w) return false;
+        return true;
+    }
+    ~Plan() {
+        if (exec) cudaGraphExecDestroy(exec);
+        for (void* p : owned) cudaFree(p);
+    }
 };
 
 }  // namespace mg
@@ -114,10 +138,12 @@ struct moge_engine {
     ConvW fold0;                      // taps-concat GEMM: (output projections folded into neck.input_blocks.0)
     StackW neck, heads[3];            // heads: points, normal, mask
     std::vector<const float*> mlp_w, mlp_b;
-    std::vector<std::unique_ptr<Plan>> plans;
+    std::vector<std::unique_ptr<Plan>> plans;      // LRU order (most recently used last), at most kMaxPlans
     Plan* last_plan = nullptr;
+    std::vector<void*> temps;         // load-time scratch (fp32 folds), freed at the end of finalize
     bool use_graphs = true;
     bool use_2cta = false;
+    bool neck_fold = false;       // last neck level folded through the heads (EPI_NECKOUT); decided at finalize
     bool ln_fold = true;          // LayerNorm folded into qkv / fc1; MOGE_B200_LNFOLD=0: separate layernorm kernel
     cudaStream_t own_stream = nullptr;
     cudaEvent_t ev_in = nullptr, ev_out = nullptr;
@@ -125,6 +151,11 @@ struct moge_engine {
     int alloc(void** p, size_t bytes) {
         CUDA_TRY(cudaMalloc(p, bytes ? bytes : 16));
         owned.push_back(*p);
+        return 0;
+    }
+    int alloc_temp(void** p, size_t bytes) {
+        CUDA_TRY(cudaMalloc(p, bytes ? bytes : 16));
+        temps.push_back(*p);
         return 0;
     }
 };
@@ -192,7 +223,7 @@ static int pack_conv3(moge_engine* e, const std::string& wkey, int Cout, int Cin
     int Nrows = Cout;
     if (up2) {      // bilinear x2 folded into the conv: 4 output phases, run on the low-resolution grid (pack.cu)
         float* wexp;
-        MG_TRY(e->alloc(reinterpret_cast<void**>(&wexp), static_cast<size_t>(4) * Cout * Cin * 9 * 4));
+        MG_TRY(e->alloc_temp(reinterpret_cast<void**>(&wexp), static_cast<size_t>(4) * Cout * Cin * 9 * 4));
         MG_TRY(launch_up2_expand(w->p, wexp, Cout, Cin, st));
         wsrc = wexp;
         Nrows = 4 * Cout;
@@ -221,7 +252,7 @@ static int pack_conv3(moge_engine* e, const std::string& wkey, int Cout, int Cin
 }
 
 static int pack_stack(moge_engine* e, const std::string& name, const moge_stack_config_t& sc, bool is_neck, StackW* sw,
-                      cudaStream_t st) {
+                      cudaStream_t st, const float* waux_all = nullptr) {
     const int L = sc.num_levels;
     sw->res.assign(L, {});
     sw->convT.assign(L, ConvW());
@@ -278,6 +309,41 @@ static int pack_stack(moge_engine* e, const std::string& name, const moge_stack_
         if (!fold_head_out) {
             if (is_neck) {
                 if (sc.dim_in[l + 1] != 2) return set_error("neck: dim_in[%d] must be 2 (UV planes)", l + 1);
+                if (waux_all != nullptr && l + 1 == L - 1) {
+                    // Last neck level folded through the heads (EPI_NECKOUT).  The level-(L-1) neck map m = conv3x3(up2(x)) + b + Wuv uv
+                    // is consumed ONLY by the heads' last-level input blocks and, with no nonlinearity in between, by their output
+                    // blocks: head k-th component += waux_all[k, :] m.  Push waux_all through the (linear) conv: a 3x3 conv with
+                    // 4 phases x 8 components on the low-resolution grid; the 32-channel map at the 16x grid is never materialised.
+                    const int Cn = C[l + 1], K9 = conv_cin * 9;
+                    const RawWeight *wc, *wi;
+                    const float *bc, *bi;
+                    MG_TRY(get_raw(e, rs + ".1.weight", &wc, {Cn, conv_cin, 3, 3}));
+                    MG_TRY(vec(e, rs + ".1.bias", Cn, &bc));
+                    MG_TRY(get_raw(e, in_key + ".weight", &wi, {Cn, 2, 1, 1}));
+                    MG_TRY(vec(e, in_key + ".bias", Cn, &bi));
+                    float *wexp, *wfold, *bsum, *wuv;
+                    MG_TRY(e->alloc_temp(reinterpret_cast<void**>(&wexp), static_cast<size_t>(4) * Cn * K9 * 4));
+                    MG_TRY(launch_up2_expand(wc->p, wexp, Cn, conv_cin, st));                    // rows (phase, channel)
+                    MG_TRY(e->alloc_temp(reinterpret_cast<void**>(&wfold), static_cast<size_t>(32) * K9 * 4));
+                    for (int ph = 0; ph < 4; ++ph)
+                        MG_TRY(launch_sgemm(waux_all, Cn, wexp + static_cast<size_t>(ph) * Cn * K9, K9, wfold + static_cast<size_t>(ph) * 8 * K9, K9, 8, K9, Cn, 0, st));
+                    ConvW& no = sw->neckout;
+                    no.N = 32; no.cin = conv_cin; no.taps = 9; no.Ktot = K9;
+                    MG_TRY(e->alloc(&no.w, static_cast<size_t>(32) * K9 * 2));
+                    MG_TRY(launch_pack_conv(wfold, no.w, e->bf16, 32, conv_cin, 9, K9, 0, st));
+                    MG_TRY(sum_bias(e, bc, bi, Cn, &bsum, st));
+                    MG_TRY(e->alloc(reinterpret_cast<void**>(&no.bias), 8 * 4));
+                    MG_TRY(launch_sgemm(waux_all, Cn, bsum, 1, no.bias, 1, 8, 1, Cn, 0, st));
+                    MG_TRY(e->alloc_temp(reinterpret_cast<void**>(&wuv), 2 * Cn * 4));
+                    vec_combine_kernel<<<(Cn + 255) / 256, 256, 0, st>>>(wuv, wi->p, 2, nullptr, Cn);
+                    vec_combine_kernel<<<(Cn + 255) / 256, 256, 0, st>>>(wuv + Cn, wi->p + 1, 2, nullptr, Cn);
+                    CUDA_TRY(cudaGetLastError());
+                    MG_TRY(e->alloc(reinterpret_cast<void**>(&no.wu), 8 * 4));
+                    MG_TRY(e->alloc(reinterpret_cast<void**>(&no.wv), 8 * 4));
+                    MG_TRY(launch_sgemm(waux_all, Cn, wuv, 1, no.wu, 1, 8, 1, Cn, 0, st));
+                    MG_TRY(launch_sgemm(waux_all, Cn, wuv + Cn, 1, no.wv, 1, 8, 1, Cn, 0, st));
+                    continue;
+                }
                 MG_TRY(pack_conv3(e, rs + ".1", C[l + 1], conv_cin, in_key, 0, true, &sw->post[l], st, sc.resamplers[l] == MOGE_RESAMPLE_BILINEAR));
             } else {
                 if (sc.dim_in[l + 1] <= 0) return set_error("%s: input block at level %d required", name.c_str(), l + 1);
@@ -300,12 +366,12 @@ static int pack_stack(moge_engine* e, const std::string& name, const moge_stack_
             MG_TRY(vec(e, name + ".output_blocks." + std::to_string(L - 1) + ".bias", nc, &bo));
             float *tmpw, *bsum, *bfold;
             const int K9 = conv_cin * 9;
-            MG_TRY(e->alloc(reinterpret_cast<void**>(&tmpw), static_cast<size_t>(16) * K9 * 4));
+            MG_TRY(e->alloc_temp(reinterpret_cast<void**>(&tmpw), static_cast<size_t>(16) * K9 * 4));
             CUDA_TRY(cudaMemsetAsync(tmpw, 0, static_cast<size_t>(16) * K9 * 4, st));
             if (sc.resamplers[l] != MOGE_RESAMPLE_BILINEAR) return set_error("%s: the last resampler must be bilinear", name.c_str());
             MG_TRY(launch_sgemm(wo->p, Cl, wc->p, K9, tmpw, K9, nc, K9, Cl, 0, st));          // [nc, (ci,tap)] = (nc,Cin,3,3)
             float* wexp;                                                                       // (4*nc,Cin,3,3), rows (phase, comp)
-            MG_TRY(e->alloc(reinterpret_cast<void**>(&wexp), static_cast<size_t>(16) * K9 * 4));
+            MG_TRY(e->alloc_temp(reinterpret_cast<void**>(&wexp), static_cast<size_t>(16) * K9 * 4));
             CUDA_TRY(cudaMemsetAsync(wexp, 0, static_cast<size_t>(16) * K9 * 4, st));
             MG_TRY(launch_up2_expand(tmpw, wexp, nc, conv_cin, st));
             ConvW& ho = sw->headout;
@@ -342,9 +408,12 @@ static int finalize(moge_engine* e, cudaStream_t st) {
     for (int i = 0; i < c.depth; ++i) {
         const std::string p = bb + "blocks." + std::to_string(i) + ".";
         moge_engine::Blk& b = e->blk[i];
-        MG_TRY(pack_linear(e, p + "attn.qkv.weight", 3 * D, D, D, &b.wqkv, st));
+        b.wqkv = nullptr; b.wfc1 = nullptr;
+        if (!e->ln_fold) {       // (with the LayerNorm fold only the folded copies below are ever read)
+            MG_TRY(pack_linear(e, p + "attn.qkv.weight", 3 * D, D, D, &b.wqkv, st));
+            MG_TRY(pack_linear(e, p + "mlp.fc1.weight", 4 * D, D, D, &b.wfc1, st));
+        }
         MG_TRY(pack_linear(e, p + "attn.proj.weight", D, D, D, &b.wproj, st));
-        MG_TRY(pack_linear(e, p + "mlp.fc1.weight", 4 * D, D, D, &b.wfc1, st));
         MG_TRY(pack_linear(e, p + "mlp.fc2.weight", D, 4 * D, 4 * D, &b.wfc2, st));
         MG_TRY(vec(e, p + "attn.qkv.bias", 3 * D, &b.bqkv));
         MG_TRY(vec(e, p + "attn.proj.bias", D, &b.bproj));
@@ -377,9 +446,9 @@ static int finalize(moge_engine* e, cudaStream_t st) {
         const float* b0;
         MG_TRY(vec(e, "neck.input_blocks.0.bias", C0, &b0));
         float *wf, *bf, *bp;
-        MG_TRY(e->alloc(reinterpret_cast<void**>(&wf), static_cast<size_t>(C0) * nt * D * 4));
+        MG_TRY(e->alloc_temp(reinterpret_cast<void**>(&wf), static_cast<size_t>(C0) * nt * D * 4));
         MG_TRY(e->alloc(reinterpret_cast<void**>(&bf), C0 * 4));
-        MG_TRY(e->alloc(reinterpret_cast<void**>(&bp), Do * 4));
+        MG_TRY(e->alloc_temp(reinterpret_cast<void**>(&bp), Do * 4));
         CUDA_TRY(cudaMemsetAsync(bp, 0, Do * 4, st));
         for (int j = 0; j < nt; ++j) {
             const RawWeight* pj;
@@ -402,9 +471,30 @@ static int finalize(moge_engine* e, cudaStream_t st) {
         vec_combine_kernel<<<(C0 + 255) / 256, 256, 0, st>>>(f.wv, w0->p + Do + 1, Do + 2, nullptr, C0);
         CUDA_TRY(cudaGetLastError());
     }
-    MG_TRY(pack_stack(e, "neck", c.neck, true, &e->neck, st));
     for (int i = 0; i < 3; ++i)
         if (head_cfg(e, i)->present) MG_TRY(pack_stack(e, head_name(i), *head_cfg(e, i), false, &e->heads[i], st));
+    // neck last: its final level can be folded through the heads' last-level input/output blocks (EPI_NECKOUT) when that level
+    // is a bilinear resampler + conv with no residual blocks and 32 channels (every MoGe-2 config); MOGE_B200_NECKFOLD=0 keeps
+    // the 32-channel map at the 16x grid and the per-head mat-vec instead
+    {
+        const int L = c.neck.num_levels;
+        bool any_head = false;
+        for (int i = 0; i < 3; ++i) any_head |= head_cfg(e, i)->present != 0;
+        const char* env = getenv("MOGE_B200_NECKFOLD");
+        e->neck_fold = !(env && env[0] == '0') && any_head && L >= 2 && c.neck.resamplers[L - 2] == MOGE_RESAMPLE_BILINEAR &&
+                       c.neck.num_res_blocks[L - 1] == 0 && c.neck.dim_res_blocks[L - 1] == 32 && c.neck.dim_res_blocks[L - 2] % 64 == 0;
+        float* waux_all = nullptr;
+        if (e->neck_fold) {
+            MG_TRY(e->alloc_temp(reinterpret_cast<void**>(&waux_all), 8 * 32 * 4));
+            CUDA_TRY(cudaMemsetAsync(waux_all, 0, 8 * 32 * 4, st));
+            const int row_of[3] = {0, 3, 6};          // points xyz | normal xyz | mask logit | pad
+            for (int i = 0; i < 3; ++i)
+                if (head_cfg(e, i)->present)
+                    CUDA_TRY(cudaMemcpyAsync(waux_all + row_of[i] * 32, e->heads[i].waux, static_cast<size_t>(e->heads[i].ncomp) * 32 * 4,
+                                             cudaMemcpyDeviceToDevice, st));
+        }
+        MG_TRY(pack_stack(e, "neck", c.neck, true, &e->neck, st, waux_all));
+    }
     for (int l = 0; l < c.scale_head_layers; ++l) {
         const float *w, *b;
         MG_TRY(vec(e, "scale_head." + std::to_string(2 * l) + ".weight", c.scale_head_dims[l] * c.scale_head_dims[l + 1], &w));
@@ -413,6 +503,8 @@ static int finalize(moge_engine* e, cudaStream_t st) {
         e->mlp_b.push_back(b);
     }
     CUDA_TRY(cudaStreamSynchronize(st));
+    for (void* t : e->temps) cudaFree(t);
+    e->temps.clear();
     // release the fp32 staging copies of the big matrices (vectors stay: kernels read them directly)
     for (auto& kv : e->raw) {
         const bool keep = kv.second.shape.size() <= 1 || kv.first.find("pos_embed") != std::string::npos ||
@@ -447,7 +539,8 @@ static size_t map_bytes(const Level& g, int B, int C) { return static_cast<size_
 // conv-type launch on padded NHWC maps. src/aux/skip/out buffers live in the workspace.
 static int add_conv(moge_engine* e, Plan* pl, const ConvW& cw, const void* src, const void* aux, const Level& gs, int B,
                     int epi, void* out_raw, void* out_relu, const void* skip, const Level& go, int out_ch, bool shuffle,
-                    bool uv, float su, float sv, const char* name, int ncomp = 0, const float* waux = nullptr) {
+                    bool uv, float su, float sv, const std::string& name, int ncomp = 0, const float* waux = nullptr, void* out2 = nullptr,
+                    int accum = 0) {
     UmmaParams p{};
     p.N = cw.N; p.ntaps = cw.taps; p.kb_main = cw.cin / 64; p.kb_aux = cw.caux / 64;
     p.B = B; p.H = gs.H; p.W = gs.W;
@@ -455,6 +548,7 @@ static int add_conv(moge_engine* e, Plan* pl, const ConvW& cw, const void* src, 
     p.num_m_tiles = B * p.tiles_x * p.tiles_y;
     int bn;
     if (epi == EPI_HEADOUT) bn = 16;
+    else if (epi == EPI_NECKOUT) bn = 32;
     else bn = pick_bn(cw.N, {256, 128, 64, 32});
     if (!bn) return set_error("conv: N=%d has no tile width", cw.N);
     p.num_n_tiles = cw.N / bn;
@@ -463,31 +557,21 @@ static int add_conv(moge_engine* e, Plan* pl, const ConvW& cw, const void* src, 
     p.skip = skip; p.ldo = out_ch;
     p.Ho = go.H; p.Wo = go.W; p.Hop = go.Hp; p.Wop = go.Wp;
     p.shuffle = shuffle ? 1 : 0; p.su = su; p.sv = sv;
-    if (epi == EPI_HEADOUT) { p.vec1 = waux; p.ncomp = ncomp; }
+    if (epi == EPI_HEADOUT) { p.vec1 = waux; p.ncomp = ncomp; p.accum = accum; }
+    p.out2 = out2;
     const bool bf16 = e->bf16; const int sms = e->num_sms;
     const double px = static_cast<double>(B) * gs.H * gs.W;
     const double flops = 2.0 * px * cw.N * cw.Ktot;
     double bytes = px * cw.cin * 2 + px * cw.caux * 2 + static_cast<double>(cw.N) * cw.Ktot * 2;
-    if (epi == EPI_HEADOUT) bytes += 4 * px * 32 * 2 + 4 * px * (ncomp == 1 ? 4 : 16);     // 4 output pixels per low-res pixel
+    if (epi == EPI_HEADOUT) bytes += 4 * px * (accum ? (ncomp == 1 ? 4 : 16) : 32 * 2) + 4 * px * (ncomp == 1 ? 4 : 16);     // 4 output pixels per low-res pixel
+    else if (epi == EPI_NECKOUT) bytes += 4 * px * ((out_raw ? 16 : 0) + (out_relu ? 16 : 0) + (out2 ? 4 : 0));
     else bytes += px * cw.N * 2 * ((out_raw ? 1 : 0) + (out_relu ? 1 : 0)) + (skip ? px * cw.N * 2 : 0);
     CUtensorMap ma, mx, mb;
     // C_in = 64 3x3 convs (levels 3/4): resident weights + one halo box per horizontal tap (conv64_kernel.cuh)
     const bool use64 = cw.taps == 9 && cw.cin == 64 && (cw.caux == 0 || cw.caux == 64) && gs.Hp >= 10 &&
-                       ((epi == EPI_HEADOUT && cw.N == 16) || (epi == EPI_DEC && cw.N % 64 == 0));
-    const bool use_s = use64 && epi == EPI_DEC && gs.Hp >= 18 && getenv("MOGE_B200_CONVS") != nullptr;
-    if (use_s) {       // swapped operands: M = 64 output channels, N = 256 pixels (convs_kernel.cuh)
-        p.tiles_x = (gs.W + 15) / 16; p.tiles_y = (gs.H + 15) / 16;
-        p.num_m_tiles = B * p.tiles_x * p.tiles_y;
-        p.num_n_tiles = cw.N / 64;
-        MG_TRY(make_map_nhwc(&ma, src, cw.cin, gs.Wp, gs.Hp, B, 18));
-        if (cw.caux) MG_TRY(make_map_nhwc(&mx, aux, cw.caux, gs.Wp, gs.Hp, B, 16));
-        else mx = ma;
-        MG_TRY(make_map_2d(&mb, cw.w, cw.Ktot, cw.N, cw.Ktot, 64));
-        pl->ops.add([=](cudaStream_t st) { return launch_convs(epi, bf16, ma, mx, mb, p, sms, st); }, name, flops, bytes);
-        return 0;
-    }
+                       ((epi == EPI_HEADOUT && cw.N == 16) || (epi == EPI_NECKOUT && cw.N == 32) || (epi == EPI_DEC && cw.N % 64 == 0));
     if (use64) {
-        const int bn64 = (epi == EPI_HEADOUT) ? 16 : 64;
+        const int bn64 = (epi == EPI_HEADOUT) ? 16 : (epi == EPI_NECKOUT) ? 32 : 64;
         p.num_n_tiles = cw.N / bn64;
         MG_TRY(make_map_nhwc(&ma, src, cw.cin, gs.Wp, gs.Hp, B, 10));
         if (cw.caux) MG_TRY(make_map_nhwc(&mx, aux, cw.caux, gs.Wp, gs.Hp, B, 8));
@@ -524,8 +608,8 @@ struct LnIO {                     // LayerNorm-fold plumbing of one linear (see 
     const float* ln_rstd = nullptr;       // consumer (EPI_STORE16 / EPI_GELU16)
 };
 static int add_linear(moge_engine* e, Plan* pl, const void* A, int M, int K, int lda, const void* W, int N, int epi,
-                      void* out, const float* bias, const float* v1, int ldo, const char* name, int T = 0, int gridw = 0,
-                      const LnIO* ln = nullptr) {
+                      void* out, const float* bias, const float* v1, int ldo, const std::string& name, int T = 0, int gridw = 0,
+                      const LnIO* ln = nullptr, int force_bn = 0, int* bn_out = nullptr) {
     UmmaParams p{};
     p.M = M; p.N = N; p.ntaps = 1; p.kb_main = (K + 63) / 64; p.kb_aux = 0;
     p.num_m_tiles = (M + TILE_M - 1) / TILE_M;
@@ -533,6 +617,8 @@ static int add_linear(moge_engine* e, Plan* pl, const void* A, int M, int K, int
     if (!bn) return set_error("linear: N=%d must be a multiple of 128", N);
     // small batches: when 128x256 tiles cannot fill the SMs, halve the tile width (N = 128 MMAs still run at N/2 cycles)
     if (bn == 256 && p.num_m_tiles * (N / 256) * 4 < e->num_sms * 3) bn = 128;
+    if (force_bn) bn = force_bn;
+    if (bn_out) *bn_out = bn;
     p.num_n_tiles = N / bn;
     p.out0 = out; p.bias = bias; p.vec1 = v1; p.ldo = ldo; p.T = T; p.W = gridw;
     double ln_extra_bytes = 0;
@@ -540,7 +626,7 @@ static int add_linear(moge_engine* e, Plan* pl, const void* A, int M, int K, int
         const int parts = N / (bn / 2);             // every ROWS kernel has 8 epilogue warps: column groups of BN/2
         p.stats_ld = kStatsLd;
         if (ln->x16) {
-            if (parts > kStatsLd) return set_error("linear %s: %d statistics groups per row > %d", name, parts, kStatsLd);
+            if (parts > kStatsLd) return set_error("linear %s: %d statistics groups per row > %d", name.c_str(), parts, kStatsLd);
             p.x16 = ln->x16; p.stats_out = ln->stats_out;
             if (ln->parts_out) *ln->parts_out = parts;
             ln_extra_bytes = static_cast<double>(M) * N * 2;
@@ -573,16 +659,12 @@ struct StackBufs {     // per-level scratch maps of one ConvStack
 
 static int plan_stack(moge_engine* e, Plan* pl, const char* sname, const moge_stack_config_t& sc, const StackW& sw, bool is_neck, int B, int h,
                       int w, float su, float sv, StackBufs& sb, const std::vector<void*>& neck_out, void* x0_raw, void* x0_relu,
-                      void* lowres_out) {
+                      void* lowres_out, void* const* neck_lowres = nullptr) {
     const int L = sc.num_levels;
     const int* C = sc.dim_res_blocks;
     void* x_raw = x0_raw;
     void* x_relu = x0_relu;
-    static std::vector<std::unique_ptr<std::string>> names;      // op names outlive the plan
-    auto nm = [&](const char* kind, int l) {
-        names.emplace_back(new std::string(std::string(kind) + "." + sname + ".l" + std::to_string(l)));
-        return names.back()->c_str();
-    };
+    auto nm = [&](const char* kind, int l) { return std::string(kind) + "." + sname + ".l" + std::to_string(l); };
     for (int l = 0; l < L; ++l) {
         const Level g = level_geom(h, w, l);
         const int nres = sc.num_res_blocks[l];
@@ -606,8 +688,15 @@ static int plan_stack(moge_engine* e, Plan* pl, const char* sname, const moge_st
             // bilinear x2 + 3x3 conv run as ONE low-resolution conv with 4 output phases (weights expanded at load time)
             const bool need_relu_b = sc.num_res_blocks[l + 1] > 0;
             if (tail) {
-                MG_TRY(add_conv(e, pl, sw.headout, x_raw, nullptr, g, B, EPI_HEADOUT, lowres_out, nullptr, neck_out[l + 1], gn, 0, false, false, 0, 0,
-                                nm("conv3x3up2.headout", l + 1), sw.ncomp, sw.waux));
+                const bool acc = e->neck_fold;
+                MG_TRY(add_conv(e, pl, sw.headout, x_raw, nullptr, g, B, EPI_HEADOUT, lowres_out, nullptr, acc ? nullptr : neck_out[l + 1], gn, 0, false,
+                                false, 0, 0, nm("conv3x3up2.headout", l + 1), sw.ncomp, acc ? nullptr : sw.waux, nullptr, acc ? 1 : 0));
+                break;
+            }
+            if (is_neck && e->neck_fold && l + 1 == L - 1) {
+                // the neck's last level goes straight into the heads' output maps (folded through their last input/output blocks)
+                MG_TRY(add_conv(e, pl, sw.neckout, x_raw, nullptr, g, B, EPI_NECKOUT, neck_lowres[0], neck_lowres[1], nullptr, gn, 0, false, true, su, sv,
+                                nm("conv3x3up2.neckout", l + 1), 0, nullptr, neck_lowres[2]));
                 break;
             }
             MG_TRY(add_conv(e, pl, sw.post[l], x_raw, nullptr, g, B, EPI_DEC, sb.x_raw[l + 1], need_relu_b ? sb.x_relu[l + 1] : nullptr, nullptr, gn,
@@ -626,42 +715,58 @@ static int plan_stack(moge_engine* e, Plan* pl, const char* sname, const moge_st
     return 0;
 }
 
-static int build_plan(moge_engine* e, Plan* pl, bool dry, size_t* bytes_out) {
+// Workspace layout + launch list of one call shape (a list of shape groups).  `dry`: only the byte count.
+static int build_plan(moge_engine* e, Plan* pl, bool dry, size_t* bytes_out, cudaStream_t upload_stream = nullptr) {
     const moge_config_t& c = e->cfg;
-    const int B = pl->B, h = pl->h, w = pl->w, H = pl->H, W = pl->W;
-    const int D = c.embed_dim, T = h * w, N = T + 1, M = B * N;
+    const int D = c.embed_dim;
     const bool bf16 = e->bf16;
+    const int G = static_cast<int>(pl->groups.size());
+    long M = 0, TT = 0;             // packed token rows (with cls) / patch tokens over all groups
+    int imgs = 0;
+    for (auto& g : pl->groups) {
+        g.img0 = imgs; g.row0 = M;
+        imgs += g.B;
+        M += static_cast<long>(g.B) * (g.h * g.w + 1);
+        TT += static_cast<long>(g.B) * g.h * g.w;
+    }
+    if (M > (1L << 30)) return set_error("too many tokens in one call (%ld)", M);
     WsAlloc ws(dry ? nullptr : pl->ws);
-    // ---- encoder buffers
-    void* patches = ws.take(static_cast<size_t>(B) * T * 592 * 2);
+    // ---- encoder buffers (all groups packed back to back)
+    uint8_t* patches = static_cast<uint8_t*>(ws.take(static_cast<size_t>(TT) * 592 * 2));
     float* x = static_cast<float*>(ws.take(static_cast<size_t>(M) * D * 4));
-    void* ln = ws.take(static_cast<size_t>(M) * D * 2);          // LN output, or (LN fold) the rounded residual rows x16
+    uint8_t* ln = static_cast<uint8_t*>(ws.take(static_cast<size_t>(M) * D * 2));          // LN output, or (LN fold) the rounded residual rows x16
     float2* stats = static_cast<float2*>(ws.take(static_cast<size_t>(M) * kStatsLd * 8));
     float* rstd = static_cast<float*>(ws.take(static_cast<size_t>(M) * 4));
     void* qkv = ws.take(static_cast<size_t>(M) * 3 * D * 2);
     void* att = ws.take(static_cast<size_t>(M) * D * 2);
     void* hid = ws.take(static_cast<size_t>(M) * 4 * D * 2);
-    void* taps = ws.take(static_cast<size_t>(B) * T * c.num_taps * D * 2);
-    float* cls = static_cast<float*>(ws.take(static_cast<size_t>(B) * D * 4));
-    float* mlp_scratch = static_cast<float*>(ws.take(static_cast<size_t>(2) * B * 4096 * 4));
-    // ---- decoder buffers
+    uint8_t* taps = static_cast<uint8_t*>(ws.take(static_cast<size_t>(TT) * c.num_taps * D * 2));
+    float* cls = static_cast<float*>(ws.take(static_cast<size_t>(imgs) * D * 4));
+    float* mlp_scratch = static_cast<float*>(ws.take(static_cast<size_t>(2) * imgs * 4096 * 4));
+    // ---- decoder buffers: the groups run one after the other through ONE set of maps sized for the largest group
     const int L = c.neck.num_levels;
-    std::vector<void*> neck_out(L, nullptr);
     auto alloc_stack = [&](const moge_stack_config_t& sc, StackBufs& sb) {
         sb.x_raw.assign(L, nullptr); sb.x_relu.assign(L, nullptr); sb.y_relu.assign(L, nullptr); sb.t_up.assign(L, nullptr);
         for (int l = 0; l < L; ++l) {
-            const Level g = level_geom(h, w, l);
             const int Cl = sc.dim_res_blocks[l];
-            sb.x_raw[l] = ws.take(map_bytes(g, B, Cl));
-            if (sc.num_res_blocks[l] > 0) {
-                sb.x_relu[l] = ws.take(map_bytes(g, B, Cl));
-                sb.y_relu[l] = ws.take(map_bytes(g, B, Cl));
-            }
             // t_up[l]: resampler output feeding the 3x3 conv of level l (channels: convT -> C[l], bilinear -> C[l-1]);
             // doubles as the second raw map of the residual ping-pong.
             int ct = Cl;
             if (l > 0 && sc.resamplers[l - 1] == MOGE_RESAMPLE_BILINEAR) ct = std::max(Cl, sc.dim_res_blocks[l - 1]);
-            sb.t_up[l] = ws.take(map_bytes(g, B, ct));
+            size_t sz = 0, szt = 0;
+            for (const auto& g : pl->groups) {
+                const Level lg = level_geom(g.h, g.w, l);
+                sz = std::max(sz, map_bytes(lg, g.B, Cl));
+                szt = std::max(szt, map_bytes(lg, g.B, ct));
+            }
+            const bool folded_last = e->neck_fold && l == L - 1;      // with the neck fold no 16x-grid feature map exists at all
+            if (folded_last) continue;
+            sb.x_raw[l] = ws.take(sz);
+            if (sc.num_res_blocks[l] > 0) {
+                sb.x_relu[l] = ws.take(sz);
+                sb.y_relu[l] = ws.take(sz);
+            }
+            sb.t_up[l] = ws.take(szt);
         }
     };
     StackBufs nb, hb;
@@ -670,37 +775,90 @@ static int build_plan(moge_engine* e, Plan* pl, bool dry, size_t* bytes_out) {
     bool any_head = false;
     for (int i = 0; i < 3; ++i) any_head |= head_cfg(e, i)->present != 0;
     if (any_head) alloc_stack(*head_cfg(e, c.points_head.present ? 0 : c.normal_head.present ? 1 : 2), hb);
-    const Level gl = level_geom(h, w, L - 1);
-    float4* pts_lr = c.points_head.present ? static_cast<float4*>(ws.take(static_cast<size_t>(B) * gl.H * gl.W * 16)) : nullptr;
-    float4* nrm_lr = c.normal_head.present ? static_cast<float4*>(ws.take(static_cast<size_t>(B) * gl.H * gl.W * 16)) : nullptr;
-    float* msk_lr = c.mask_head.present ? static_cast<float*>(ws.take(static_cast<size_t>(B) * gl.H * gl.W * 4)) : nullptr;
+    // low-resolution fp32 head outputs, PER GROUP (read by the phase-2 output kernels after every group's decoder has run)
+    std::vector<float4*> pts_lr(G, nullptr), nrm_lr(G, nullptr);
+    std::vector<float*> msk_lr(G, nullptr);
+    for (int gi = 0; gi < G; ++gi) {
+        const Group& g = pl->groups[gi];
+        const Level gl = level_geom(g.h, g.w, L - 1);
+        const size_t px = static_cast<size_t>(g.B) * gl.H * gl.W;
+        if (c.points_head.present) pts_lr[gi] = static_cast<float4*>(ws.take(px * 16));
+        if (c.normal_head.present) nrm_lr[gi] = static_cast<float4*>(ws.take(px * 16));
+        if (c.mask_head.present) msk_lr[gi] = static_cast<float*>(ws.take(px * 4));
+    }
     if (bytes_out) *bytes_out = ws.off + 1024;
     if (dry) return 0;
     if (ws.off > pl->ws_bytes) return set_error("workspace too small: need %zu bytes, got %zu", ws.off, pl->ws_bytes);
 
-    const float aspect = static_cast<float>(W) / H;
-    const float su = aspect / sqrtf(1.f + aspect * aspect), sv = 1.f / sqrtf(1.f + aspect * aspect);
     Plan* P = pl;
-    // ---- K1: resize + normalise + patchify (reads the image pointer bound at forward time)
-    pl->ops.add([=](cudaStream_t st) { return launch_preprocess(P->image, P->image_dtype, B, H, W, h, w, patches, 592, bf16, st); },
-                "preprocess", 0, static_cast<double>(B) * 3 * H * W * 4 + static_cast<double>(B) * T * 592 * 2);
-    // ---- K2/K3: patch embed + pos embed; cls rows
     const bool fold = e->ln_fold;
+    const int sms = e->num_sms;
+    const std::string gsuffix_none;
+    auto gname = [&](const char* base, int gi) { return G == 1 ? std::string(base) : std::string(base) + ".g" + std::to_string(gi); };
+    // ---- per group: K1 resize + normalise + patchify (phase 0: reads the caller's image), K2/K3 patch embed + pos embed, cls rows
     int parts_x = 0;              // column groups per row of the statistics the NEXT consumer reads
-    LnIO prod; prod.x16 = ln; prod.stats_out = stats; prod.parts_out = &parts_x;
-    MG_TRY(add_linear(e, pl, patches, B * T, 592, 592, e->w_patch, D, EPI_PATCH, x, nullptr, pl->pos_table, D, "gemm.patch_embed", T, w,
-                      fold ? &prod : nullptr));
-    pl->ops.add([=](cudaStream_t st) { return launch_init_cls(x, P->cls_row, B, N, D, st); }, "init_cls");
-    if (fold) {
-        const int parts0 = parts_x;
-        pl->ops.add([=](cudaStream_t st) {
-            return launch_ln_prepare(x, B, static_cast<long>(N) * D, D, ln, static_cast<long>(N) * D, stats, static_cast<long>(N) * kStatsLd, parts0, bf16, st);
-        }, "ln_prepare.cls");
+    int bn_patch = 0;
+    {   // one tile width for every group's patch-embed GEMM (the statistics layout must agree): chosen from the total row count
+        const int mt = static_cast<int>((TT + TILE_M - 1) / TILE_M);
+        bn_patch = pick_bn(D, {256, 128});
+        if (!bn_patch) return set_error("embed_dim=%d must be a multiple of 128", D);
+        if (bn_patch == 256 && mt * (D / 256) * 4 < sms * 3) bn_patch = 128;
     }
+    long prow = 0;                // first patch row of the group in `patches` / `taps`
+    std::vector<long> prow0(G);
+    for (int gi = 0; gi < G; ++gi) {
+        const Group& g = pl->groups[gi];
+        const int B = g.B, H = g.H, W = g.W, h = g.h, w = g.w, T = h * w, N = T + 1;
+        prow0[gi] = prow;
+        uint8_t* patches_g = patches + static_cast<size_t>(prow) * 592 * 2;
+        pl->ops.add([=](cudaStream_t st) { return launch_preprocess(P->groups[gi].image, P->groups[gi].image_dtype, B, H, W, h, w, patches_g, 592, bf16, st); },
+                    gname("preprocess", gi), 0, static_cast<double>(B) * 3 * H * W * 4 + static_cast<double>(B) * T * 592 * 2, 0);
+        prow += static_cast<long>(B) * T;
+    }
+    for (int gi = 0; gi < G; ++gi) {
+        const Group& g = pl->groups[gi];
+        const int B = g.B, h = g.h, w = g.w, T = h * w, N = T + 1;
+        uint8_t* patches_g = patches + static_cast<size_t>(prow0[gi]) * 592 * 2;
+        float* x_g = x + static_cast<size_t>(g.row0) * D;
+        uint8_t* ln_g = ln + static_cast<size_t>(g.row0) * D * 2;
+        float2* stats_g = stats + static_cast<size_t>(g.row0) * kStatsLd;
+        LnIO prod; prod.x16 = ln_g; prod.stats_out = stats_g; prod.parts_out = &parts_x;
+        MG_TRY(add_linear(e, pl, patches_g, B * T, 592, 592, e->w_patch, D, EPI_PATCH, x_g, nullptr, g.pos_table, D, gname("gemm.patch_embed", gi), T, w,
+                          fold ? &prod : nullptr, bn_patch));
+        pl->ops.add([=](cudaStream_t st) { return launch_init_cls(x_g, P->cls_row, B, N, D, st); }, gname("init_cls", gi));
+        if (fold) {
+            const int parts0 = parts_x;
+            pl->ops.add([=](cudaStream_t st) {
+                return launch_ln_prepare(x_g, B, static_cast<long>(N) * D, D, ln_g, static_cast<long>(N) * D, stats_g, static_cast<long>(N) * kStatsLd, parts0, bf16, st);
+            }, gname("ln_prepare.cls", gi));
+        }
+    }
+    const int Mi = static_cast<int>(M);
+    LnIO prod; prod.x16 = ln; prod.stats_out = stats; prod.parts_out = &parts_x;
     auto add_rstd = [&](int parts) {      // per-row rstd of the rows the last producer wrote
-        pl->ops.add([=](cudaStream_t st) { return launch_ln_rstd(stats, kStatsLd, parts, M, D, rstd, st); }, "ln_rstd", 0, static_cast<double>(M) * (parts * 8 + 4));
+        pl->ops.add([=](cudaStream_t st) { return launch_ln_rstd(stats, kStatsLd, parts, Mi, D, rstd, st); }, "ln_rstd", 0, static_cast<double>(M) * (parts * 8 + 4));
     };
-    // ---- transformer blocks
+    // ---- attention work list (image, head, query-tile pair) over the packed rows, cost-balanced over the SMs
+    {
+        std::vector<int> r0, nn;
+        for (const auto& g : pl->groups)
+            for (int b = 0; b < g.B; ++b) { r0.push_back(static_cast<int>(g.row0 + static_cast<long>(b) * (g.h * g.w + 1))); nn.push_back(g.h * g.w + 1); }
+        attention_work_list(r0.data(), nn.data(), imgs, c.num_heads, sms, &pl->att_items, &pl->att_ranges);
+    }
+    AttnItem* items_dev = nullptr;
+    int2* ranges_dev = nullptr;
+    const int att_ctas = static_cast<int>(pl->att_ranges.size());
+    {
+        CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&items_dev), pl->att_items.size() * sizeof(AttnItem) + 16));
+        pl->owned.push_back(items_dev);
+        CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&ranges_dev), pl->att_ranges.size() * sizeof(int2) + 16));
+        pl->owned.push_back(ranges_dev);
+        CUDA_TRY(cudaMemcpyAsync(items_dev, pl->att_items.data(), pl->att_items.size() * sizeof(AttnItem), cudaMemcpyHostToDevice, upload_stream));
+        CUDA_TRY(cudaMemcpyAsync(ranges_dev, pl->att_ranges.data(), pl->att_ranges.size() * sizeof(int2), cudaMemcpyHostToDevice, upload_stream));
+    }
+    double att_flops = 0;
+    for (const auto& g : pl->groups) { const double N = g.h * g.w + 1; att_flops += 4.0 * g.B * N * N * D; }
+    // ---- transformer blocks: ONE launch per linear / attention over the packed rows of every group
     int tap_idx = 0;
     for (int i = 0; i < c.depth; ++i) {
         const moge_engine::Blk& b = e->blk[i];
@@ -708,116 +866,163 @@ static int build_plan(moge_engine* e, Plan* pl, bool dry, size_t* bytes_out) {
         if (fold) {
             if (i == 0) add_rstd(parts_x);
             LnIO cons; cons.ln_rstd = rstd;
-            MG_TRY(add_linear(e, pl, ln, M, D, D, b.wqkv_ln, 3 * D, EPI_STORE16, qkv, b.b_qkv_ln, nullptr, 3 * D, "gemm.qkv", 0, 0, &cons));
+            MG_TRY(add_linear(e, pl, ln, Mi, D, D, b.wqkv_ln, 3 * D, EPI_STORE16, qkv, b.b_qkv_ln, nullptr, 3 * D, "gemm.qkv", 0, 0, &cons));
         } else {
-            pl->ops.add([=](cudaStream_t st) { return launch_layernorm(x, b.ln1g, b.ln1b, ln, M, D, D, 0, 0, N, nullptr, bf16, st); }, "layernorm", 0, ln_bytes);
-            MG_TRY(add_linear(e, pl, ln, M, D, D, b.wqkv, 3 * D, EPI_STORE16, qkv, b.bqkv, nullptr, 3 * D, "gemm.qkv"));
+            pl->ops.add([=](cudaStream_t st) { return launch_layernorm(x, b.ln1g, b.ln1b, ln, Mi, D, D, 0, 0, 1, nullptr, bf16, st); }, "layernorm", 0, ln_bytes);
+            MG_TRY(add_linear(e, pl, ln, Mi, D, D, b.wqkv, 3 * D, EPI_STORE16, qkv, b.bqkv, nullptr, 3 * D, "gemm.qkv"));
         }
         {
             CUtensorMap mq;
-            MG_TRY(make_map_3d(&mq, qkv, 3 * D, N, B, 128));
+            MG_TRY(make_map_2d(&mq, qkv, 3 * static_cast<uint64_t>(D), M, 3 * static_cast<uint64_t>(D), 128));
             const int heads = c.num_heads;
-            pl->ops.add([=](cudaStream_t st) { return launch_attention(mq, att, B, N, D, heads, bf16, st); }, "attention",
-                        4.0 * B * static_cast<double>(N) * N * D, static_cast<double>(M) * D * 8);
+            pl->ops.add([=](cudaStream_t st) { return launch_attention(mq, att, items_dev, ranges_dev, att_ctas, D, heads, bf16, st); }, "attention",
+                        att_flops, static_cast<double>(M) * D * 8);
         }
         if (fold) {
-            MG_TRY(add_linear(e, pl, att, M, D, D, b.wproj, D, EPI_RESID, x, b.bproj, b.g1, D, "gemm.proj", 0, 0, &prod));
+            MG_TRY(add_linear(e, pl, att, Mi, D, D, b.wproj, D, EPI_RESID, x, b.bproj, b.g1, D, "gemm.proj", 0, 0, &prod));
             add_rstd(parts_x);
             LnIO cons; cons.ln_rstd = rstd;
-            MG_TRY(add_linear(e, pl, ln, M, D, D, b.wfc1_ln, 4 * D, EPI_GELU16, hid, b.b_fc1_ln, nullptr, 4 * D, "gemm.fc1", 0, 0, &cons));
-            MG_TRY(add_linear(e, pl, hid, M, 4 * D, 4 * D, b.wfc2, D, EPI_RESID, x, b.bfc2, b.g2, D, "gemm.fc2", 0, 0, (i + 1 < c.depth) ? &prod : nullptr));
+            MG_TRY(add_linear(e, pl, ln, Mi, D, D, b.wfc1_ln, 4 * D, EPI_GELU16, hid, b.b_fc1_ln, nullptr, 4 * D, "gemm.fc1", 0, 0, &cons));
+            MG_TRY(add_linear(e, pl, hid, Mi, 4 * D, 4 * D, b.wfc2, D, EPI_RESID, x, b.bfc2, b.g2, D, "gemm.fc2", 0, 0, (i + 1 < c.depth) ? &prod : nullptr));
             if (i + 1 < c.depth) add_rstd(parts_x);
         } else {
-            MG_TRY(add_linear(e, pl, att, M, D, D, b.wproj, D, EPI_RESID, x, b.bproj, b.g1, D, "gemm.proj"));
-            pl->ops.add([=](cudaStream_t st) { return launch_layernorm(x, b.ln2g, b.ln2b, ln, M, D, D, 0, 0, N, nullptr, bf16, st); }, "layernorm", 0, ln_bytes);
-            MG_TRY(add_linear(e, pl, ln, M, D, D, b.wfc1, 4 * D, EPI_GELU16, hid, b.bfc1, nullptr, 4 * D, "gemm.fc1"));
-            MG_TRY(add_linear(e, pl, hid, M, 4 * D, 4 * D, b.wfc2, D, EPI_RESID, x, b.bfc2, b.g2, D, "gemm.fc2"));
+            MG_TRY(add_linear(e, pl, att, Mi, D, D, b.wproj, D, EPI_RESID, x, b.bproj, b.g1, D, "gemm.proj"));
+            pl->ops.add([=](cudaStream_t st) { return launch_layernorm(x, b.ln2g, b.ln2b, ln, Mi, D, D, 0, 0, 1, nullptr, bf16, st); }, "layernorm", 0, ln_bytes);
+            MG_TRY(add_linear(e, pl, ln, Mi, D, D, b.wfc1, 4 * D, EPI_GELU16, hid, b.bfc1, nullptr, 4 * D, "gemm.fc1"));
+            MG_TRY(add_linear(e, pl, hid, Mi, 4 * D, 4 * D, b.wfc2, D, EPI_RESID, x, b.bfc2, b.g2, D, "gemm.fc2"));
         }
         if (tap_idx < c.num_taps && c.taps[tap_idx] == i) {
             const int j = tap_idx++;
             const bool lasttap = (j == c.num_taps - 1);
             const int ld = c.num_taps * D;
             const float* ng = e->norm_g; const float* nbv = e->norm_b;
-            pl->ops.add([=](cudaStream_t st) {
-                return launch_layernorm(x, ng, nbv, taps, M, D, ld, j * D, 1, N, lasttap ? cls : nullptr, bf16, st);
-            }, "layernorm.tap", 0, ln_bytes);
+            for (int gi = 0; gi < G; ++gi) {
+                const Group& g = pl->groups[gi];
+                const int N = g.h * g.w + 1, rows = g.B * N;
+                const float* x_g = x + static_cast<size_t>(g.row0) * D;
+                uint8_t* taps_g = taps + static_cast<size_t>(prow0[gi]) * ld * 2;
+                float* cls_g = cls + static_cast<size_t>(g.img0) * D;
+                pl->ops.add([=](cudaStream_t st) {
+                    return launch_layernorm(x_g, ng, nbv, taps_g, rows, D, ld, j * D, 1, N, lasttap ? cls_g : nullptr, bf16, st);
+                }, gname("layernorm.tap", gi), 0, static_cast<double>(rows) * D * 6);
+            }
         }
     }
     if (tap_idx != c.num_taps) return set_error("intermediate_layers must be increasing block indices < depth");
-    // ---- scale head
-    if (c.scale_head_layers > 0) {
-        std::vector<const float*> mw = e->mlp_w, mb = e->mlp_b;
-        std::vector<int> dims(c.scale_head_dims, c.scale_head_dims + c.scale_head_layers + 1);
-        const int nl = c.scale_head_layers;
-        for (int d : dims) if (d > 4096) return set_error("scale head width %d > 4096", d);
-        pl->ops.add([=](cudaStream_t st) {
-            if (!P->scale) return 0;
-            return launch_scale_head(cls, mw.data(), mb.data(), dims.data(), nl, B, P->scale, mlp_scratch, st);
-        }, "scale_head");
+    // ---- decoder, group by group
+    for (int gi = 0; gi < G; ++gi) {
+        const Group& g = pl->groups[gi];
+        const int B = g.B, H = g.H, W = g.W, h = g.h, w = g.w, T = h * w;
+        const float aspect = static_cast<float>(W) / H;
+        const float su = aspect / sqrtf(1.f + aspect * aspect), sv = 1.f / sqrtf(1.f + aspect * aspect);
+        uint8_t* taps_g = taps + static_cast<size_t>(prow0[gi]) * c.num_taps * D * 2;
+        std::vector<void*> neck_out(L, nullptr);
+        // neck level 0: folded projection GEMM over the concatenated taps (+UV rank-2 term) -> padded NHWC
+        {
+            const Level g0 = level_geom(h, w, 0);
+            const ConvW& f = e->fold0;
+            UmmaParams p{};
+            p.M = B * T; p.N = f.N; p.ntaps = 1; p.kb_main = f.Ktot / 64; p.kb_aux = 0;
+            if (f.Ktot % 64) return set_error("num_taps*embed_dim must be a multiple of 64");
+            p.num_m_tiles = (p.M + TILE_M - 1) / TILE_M;
+            const int bn = pick_bn(f.N, {256, 128});
+            if (!bn) return set_error("neck width %d must be a multiple of 128", f.N);
+            p.num_n_tiles = f.N / bn;
+            p.B = B; p.H = h; p.W = w; p.T = T;
+            p.out0 = nb.x_raw[0]; p.out1 = c.neck.num_res_blocks[0] > 0 ? nb.x_relu[0] : nullptr;
+            p.bias = f.bias; p.vec1 = f.wu; p.vec2 = f.wv; p.ldo = f.N;
+            p.Ho = g0.H; p.Wo = g0.W; p.Hop = g0.Hp; p.Wop = g0.Wp; p.su = su; p.sv = sv;
+            CUtensorMap ma, mb;
+            MG_TRY(make_map_2d(&ma, taps_g, f.Ktot, p.M, f.Ktot, TILE_M));
+            MG_TRY(make_map_2d(&mb, f.w, f.Ktot, f.N, f.Ktot, bn));
+            pl->ops.add([=](cudaStream_t st) { return launch_umma(bn, AMODE_ROWS, EPI_DEC, bf16, ma, ma, mb, p, sms, st); }, gname("gemm.taps_proj", gi),
+                        2.0 * p.M * static_cast<double>(f.N) * f.Ktot, static_cast<double>(p.M) * f.Ktot * 2 + static_cast<double>(f.N) * f.Ktot * 2 + static_cast<double>(p.M) * f.N * 2);
+        }
+        void* neck_lowres[3] = {pts_lr[gi], nrm_lr[gi], msk_lr[gi]};
+        const std::string sfx = G == 1 ? std::string() : ".g" + std::to_string(gi);
+        MG_TRY(plan_stack(e, pl, ("neck" + sfx).c_str(), c.neck, e->neck, true, B, h, w, su, sv, nb, neck_out, nb.x_raw[0], nb.x_relu[0], nullptr, neck_lowres));
+        for (int i = 0; i < 3; ++i) {
+            const moge_stack_config_t& sc = *head_cfg(e, i);
+            if (!sc.present) continue;
+            const Level g0 = level_geom(h, w, 0);
+            const StackW& sw = e->heads[i];
+            MG_TRY(add_conv(e, pl, sw.in0, neck_out[0], nullptr, g0, B, EPI_DEC, hb.x_raw[0], sc.num_res_blocks[0] > 0 ? hb.x_relu[0] : nullptr,
+                            nullptr, g0, sc.dim_res_blocks[0], false, false, 0, 0, std::string("conv1x1.") + head_name(i) + sfx + ".l0"));
+            void* lowres = i == 0 ? static_cast<void*>(pts_lr[gi]) : i == 1 ? static_cast<void*>(nrm_lr[gi]) : static_cast<void*>(msk_lr[gi]);
+            MG_TRY(plan_stack(e, pl, (std::string(head_name(i)) + sfx).c_str(), sc, sw, false, B, h, w, su, sv, hb, neck_out, hb.x_raw[0], hb.x_relu[0], lowres));
+        }
     }
-    // ---- neck level 0: folded projection GEMM over the concatenated taps (+UV rank-2 term) -> padded NHWC
-    {
-        const Level g0 = level_geom(h, w, 0);
-        const ConvW& f = e->fold0;
-        UmmaParams p{};
-        p.M = B * T; p.N = f.N; p.ntaps = 1; p.kb_main = f.Ktot / 64; p.kb_aux = 0;
-        if (f.Ktot % 64) return set_error("num_taps*embed_dim must be a multiple of 64");
-        p.num_m_tiles = (p.M + TILE_M - 1) / TILE_M;
-        const int bn = pick_bn(f.N, {256, 128});
-        if (!bn) return set_error("neck width %d must be a multiple of 128", f.N);
-        p.num_n_tiles = f.N / bn;
-        p.B = B; p.H = h; p.W = w; p.T = T;
-        p.out0 = nb.x_raw[0]; p.out1 = c.neck.num_res_blocks[0] > 0 ? nb.x_relu[0] : nullptr;
-        p.bias = f.bias; p.vec1 = f.wu; p.vec2 = f.wv; p.ldo = f.N;
-        p.Ho = g0.H; p.Wo = g0.W; p.Hop = g0.Hp; p.Wop = g0.Wp; p.su = su; p.sv = sv;
-        CUtensorMap ma, mb;
-        MG_TRY(make_map_2d(&ma, taps, f.Ktot, p.M, f.Ktot, TILE_M));
-        MG_TRY(make_map_2d(&mb, f.w, f.Ktot, f.N, f.Ktot, bn));
-        const int sms = e->num_sms;
-        pl->ops.add([=](cudaStream_t st) { return launch_umma(bn, AMODE_ROWS, EPI_DEC, bf16, ma, ma, mb, p, sms, st); }, "gemm.taps_proj",
-                    2.0 * p.M * static_cast<double>(f.N) * f.Ktot, static_cast<double>(p.M) * f.Ktot * 2 + static_cast<double>(f.N) * f.Ktot * 2 + static_cast<double>(p.M) * f.N * 2);
-    }
-    MG_TRY(plan_stack(e, pl, "neck", c.neck, e->neck, true, B, h, w, su, sv, nb, neck_out, nb.x_raw[0], nb.x_relu[0], nullptr));
-    // ---- heads
-    for (int i = 0; i < 3; ++i) {
-        const moge_stack_config_t& sc = *head_cfg(e, i);
-        if (!sc.present) continue;
-        const Level g0 = level_geom(h, w, 0);
-        const StackW& sw = e->heads[i];
-        MG_TRY(add_conv(e, pl, sw.in0, neck_out[0], nullptr, g0, B, EPI_DEC, hb.x_raw[0], sc.num_res_blocks[0] > 0 ? hb.x_relu[0] : nullptr,
-                        nullptr, g0, sc.dim_res_blocks[0], false, false, 0, 0, i == 0 ? "conv1x1.points_head.l0" : i == 1 ? "conv1x1.normal_head.l0" : "conv1x1.mask_head.l0"));
-        void* lowres = i == 0 ? static_cast<void*>(pts_lr) : i == 1 ? static_cast<void*>(nrm_lr) : static_cast<void*>(msk_lr);
-        MG_TRY(plan_stack(e, pl, head_name(i), sc, sw, false, B, h, w, su, sv, hb, neck_out, hb.x_raw[0], hb.x_relu[0], lowres));
-    }
-    // ---- K17 fused resize + remap
-    {
+    // ---- phase 2 (caller-bound outputs): scale head, K17 fused resize + remap
+    for (int gi = 0; gi < G; ++gi) {
+        const Group& g = pl->groups[gi];
+        const int B = g.B, H = g.H, W = g.W;
+        const Level gl = level_geom(g.h, g.w, L - 1);
+        if (c.scale_head_layers > 0) {
+            std::vector<const float*> mw = e->mlp_w, mb = e->mlp_b;
+            std::vector<int> dims(c.scale_head_dims, c.scale_head_dims + c.scale_head_layers + 1);
+            const int nl = c.scale_head_layers;
+            for (int d : dims) if (d > 4096) return set_error("scale head width %d > 4096", d);
+            const float* cls_g = cls + static_cast<size_t>(g.img0) * D;
+            float* scratch_g = mlp_scratch + static_cast<size_t>(2) * g.img0 * 4096;
+            pl->ops.add([=](cudaStream_t st) {
+                if (!P->groups[gi].scale) return 0;
+                return launch_scale_head(cls_g, mw.data(), mb.data(), dims.data(), nl, B, P->groups[gi].scale, scratch_g, st);
+            }, gname("scale_head", gi), 0, 0, 2);
+        }
         const int remap = c.remap_output;
+        float4* pl_ = pts_lr[gi]; float4* nl_ = nrm_lr[gi]; float* ml_ = msk_lr[gi];
         pl->ops.add([=](cudaStream_t st) {
-            return launch_head_output(P->points ? pts_lr : nullptr, P->normal ? nrm_lr : nullptr, P->mask ? msk_lr : nullptr, B, gl.H, gl.W,
-                                      H, W, remap, P->points, P->normal, P->mask, st);
-        }, "head_output", 0, static_cast<double>(B) * H * W * 28 + static_cast<double>(B) * gl.H * gl.W * 36);
+            const Group& gg = P->groups[gi];
+            return launch_head_output(gg.points ? pl_ : nullptr, gg.normal ? nl_ : nullptr, gg.mask ? ml_ : nullptr, B, gl.H, gl.W,
+                                      H, W, remap, gg.points, gg.normal, gg.mask, st);
+        }, gname("head_output", gi), 0, static_cast<double>(B) * H * W * 28 + static_cast<double>(B) * gl.H * gl.W * 36, 2);
     }
+    // launch order: phase 0, 1, 2 (stable)
+    std::stable_sort(pl->ops.begin(), pl->ops.end(), [](const Op& a, const Op& b) { return a.phase < b.phase; });
     return 0;
 }
 
-static int get_plan(moge_engine* e, int B, int H, int W, int h, int w, void* ws, size_t ws_bytes, Plan** out, cudaStream_t st) {
-    for (auto& p : e->plans)
-        if (p->B == B && p->H == H && p->W == W && p->h == h && p->w == w && p->ws == ws) {
-            *out = p.get();
+constexpr size_t kMaxPlans = 16;
+
+// Plans are keyed on the call shape; the workspace pointer is part of what a plan bakes in (TMA descriptors), so a call with the
+// same shape but another workspace REPLACES the plan instead of orphaning it.  A plan owns its device buffers (pos tables,
+// attention work list) and frees them when it is replaced or evicted (LRU) -- after the device has drained, since launches
+// that read them may still be queued on the caller's stream.
+static int get_plan(moge_engine* e, const moge_group_t* groups, int n, void* ws, size_t ws_bytes, Plan** out, cudaStream_t st) {
+    for (size_t i = 0; i < e->plans.size(); ++i) {
+        if (!e->plans[i]->same_shape(groups, n)) continue;
+        if (e->plans[i]->ws == ws && e->plans[i]->ws_bytes == ws_bytes) {
+            std::rotate(e->plans.begin() + i, e->plans.begin() + i + 1, e->plans.end());      // most recently used last
+            *out = e->plans.back().get();
             return 0;
         }
-    if (e->plans.size() >= 16) {
+        CUDA_TRY(cudaDeviceSynchronize());
+        if (e->last_plan == e->plans[i].get()) e->last_plan = nullptr;
+        e->plans.erase(e->plans.begin() + i);
+        break;
+    }
+    if (e->plans.size() >= kMaxPlans) {
+        CUDA_TRY(cudaDeviceSynchronize());
         if (e->last_plan == e->plans.front().get()) e->last_plan = nullptr;
-        for (auto& g : e->plans.front()->graphs) cudaGraphExecDestroy(g.exec);
         e->plans.erase(e->plans.begin());
     }
     std::unique_ptr<Plan> pl(new Plan());
-    pl->B = B; pl->H = H; pl->W = W; pl->h = h; pl->w = w; pl->ws = ws; pl->ws_bytes = ws_bytes;
+    pl->ws = ws; pl->ws_bytes = ws_bytes;
     const int D = e->cfg.embed_dim;
-    MG_TRY(e->alloc(reinterpret_cast<void**>(&pl->pos_table), static_cast<size_t>(h) * w * D * 4));
-    MG_TRY(e->alloc(reinterpret_cast<void**>(&pl->cls_row), D * 4));
-    MG_TRY(launch_pos_table(e->pos_embed, e->cls_token, e->patch_bias, D, h, w, pl->pos_table, pl->cls_row, st));
-    MG_TRY(build_plan(e, pl.get(), false, nullptr));
+    void* p = nullptr;
+    CUDA_TRY(cudaMalloc(&p, D * 4));
+    pl->owned.push_back(p);
+    pl->cls_row = static_cast<float*>(p);
+    for (int i = 0; i < n; ++i) {
+        Group g;
+        g.B = groups[i].B; g.H = groups[i].H; g.W = groups[i].W; g.h = groups[i].h; g.w = groups[i].w;
+        CUDA_TRY(cudaMalloc(&p, static_cast<size_t>(g.h) * g.w * D * 4));
+        pl->owned.push_back(p);
+        g.pos_table = static_cast<float*>(p);
+        MG_TRY(launch_pos_table(e->pos_embed, e->cls_token, e->patch_bias, D, g.h, g.w, g.pos_table, pl->cls_row, st));
+        pl->groups.push_back(g);
+    }
+    MG_TRY(build_plan(e, pl.get(), false, nullptr, st));
     *out = pl.get();
     e->plans.push_back(std::move(pl));
     return 0;
@@ -882,12 +1087,12 @@ void moge_engine_destroy(moge_engine_t* e) {
     if (!e) return;
     cudaSetDevice(e->device);
     cudaDeviceSynchronize();
-    for (auto& pl : e->plans)
-        for (auto& g : pl->graphs) cudaGraphExecDestroy(g.exec);
+    e->plans.clear();            // each plan frees its graph and buffers
     if (e->own_stream) cudaStreamDestroy(e->own_stream);
     if (e->ev_in) cudaEventDestroy(e->ev_in);
     if (e->ev_out) cudaEventDestroy(e->ev_out);
     for (void* p : e->owned) cudaFree(p);
+    for (void* p : e->temps) cudaFree(p);
     for (auto& kv : e->raw) if (kv.second.p) cudaFree(kv.second.p);
     delete e;
 }
@@ -918,70 +1123,104 @@ int moge_engine_finalize(moge_engine_t* e, void* stream) {
     return finalize(e, static_cast<cudaStream_t>(stream));
 }
 
-int moge_engine_workspace_bytes(moge_engine_t* e, int B, int H, int W, int h, int w, size_t* bytes) {
-    if (!e || !bytes) return set_error("null argument");
-    if (B <= 0 || h <= 0 || w <= 0 || H <= 0 || W <= 0) return set_error("bad shape B=%d H=%d W=%d h=%d w=%d", B, H, W, h, w);
+static int check_groups(moge_engine_t* e, const moge_group_t* g, int n, bool need_ptrs) {
+    if (!e || !g) return set_error("null argument");
+    if (n <= 0 || n > 64) return set_error("number of shape groups %d out of range (1..64)", n);
+    for (int i = 0; i < n; ++i) {
+        if (g[i].B <= 0 || g[i].h <= 0 || g[i].w <= 0 || g[i].H <= 0 || g[i].W <= 0)
+            return set_error("bad shape B=%d H=%d W=%d h=%d w=%d", g[i].B, g[i].H, g[i].W, g[i].h, g[i].w);
+        if (!need_ptrs) continue;
+        if (!g[i].image) return set_error("null argument");
+        if (g[i].image_dtype != MOGE_F32 && g[i].image_dtype != MOGE_F16 && g[i].image_dtype != MOGE_BF16) return set_error("unsupported image dtype %d", g[i].image_dtype);
+        if (g[i].points && !e->cfg.points_head.present) return set_error("points requested but the model has no points head");
+        if (g[i].normal && !e->cfg.normal_head.present) return set_error("normal requested but the model has no normal head");
+        if (g[i].mask_prob && !e->cfg.mask_head.present) return set_error("mask requested but the model has no mask head");
+        if (g[i].metric_scale && e->cfg.scale_head_layers == 0) return set_error("metric_scale requested but the model has no scale head");
+    }
+    return 0;
+}
+
+int moge_engine_workspace_bytes_groups(moge_engine_t* e, const moge_group_t* groups, int n, size_t* bytes) {
+    if (!bytes) return set_error("null argument");
+    MG_TRY(check_groups(e, groups, n, false));
     Plan pl;
-    pl.B = B; pl.H = H; pl.W = W; pl.h = h; pl.w = w; pl.ws = nullptr; pl.ws_bytes = 0;
+    for (int i = 0; i < n; ++i) {
+        Group g;
+        g.B = groups[i].B; g.H = groups[i].H; g.W = groups[i].W; g.h = groups[i].h; g.w = groups[i].w;
+        pl.groups.push_back(g);
+    }
     return build_plan(e, &pl, true, bytes);
 }
 
-int moge_engine_forward(moge_engine_t* e, const void* image, int image_dtype, int B, int H, int W, int h, int w, void* workspace,
-                        size_t workspace_bytes, float* points, float* normal, float* mask_prob, float* metric_scale, void* stream) {
-    if (!e || !image || !workspace) return set_error("null argument");
+int moge_engine_workspace_bytes(moge_engine_t* e, int B, int H, int W, int h, int w, size_t* bytes) {
+    moge_group_t g{};
+    g.B = B; g.H = H; g.W = W; g.h = h; g.w = w;
+    return moge_engine_workspace_bytes_groups(e, &g, 1, bytes);
+}
+
+int moge_engine_forward_groups(moge_engine_t* e, const moge_group_t* groups, int n, void* workspace, size_t workspace_bytes, void* stream) {
+    if (!e || !workspace) return set_error("null argument");
     if (!e->finalized) return set_error("engine not finalized");
-    if (B <= 0 || h <= 0 || w <= 0 || H <= 0 || W <= 0) return set_error("bad shape B=%d H=%d W=%d h=%d w=%d", B, H, W, h, w);
+    MG_TRY(check_groups(e, groups, n, true));
     if (reinterpret_cast<uintptr_t>(workspace) & 1023) return set_error("workspace must be 1024-byte aligned");
-    if (points && !e->cfg.points_head.present) return set_error("points requested but the model has no points head");
-    if (normal && !e->cfg.normal_head.present) return set_error("normal requested but the model has no normal head");
-    if (mask_prob && !e->cfg.mask_head.present) return set_error("mask requested but the model has no mask head");
-    if (metric_scale && e->cfg.scale_head_layers == 0) return set_error("metric_scale requested but the model has no scale head");
     CUDA_TRY(cudaSetDevice(e->device));
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     Plan* pl;
-    MG_TRY(get_plan(e, B, H, W, h, w, workspace, workspace_bytes, &pl, st));
-    pl->image = image; pl->image_dtype = image_dtype;
-    pl->points = points; pl->normal = normal; pl->mask = mask_prob; pl->scale = metric_scale;
+    MG_TRY(get_plan(e, groups, n, workspace, workspace_bytes, &pl, st));
+    long tokens = 0;
+    for (int i = 0; i < n; ++i) {
+        Group& g = pl->groups[i];
+        g.image = groups[i].image; g.image_dtype = groups[i].image_dtype;
+        g.points = groups[i].points; g.normal = groups[i].normal; g.mask = groups[i].mask_prob; g.scale = groups[i].metric_scale;
+        tokens += static_cast<long>(g.B) * g.h * g.w;
+    }
     e->last_plan = pl;
-    // ---- graph replay (small batches only: at large batch the GPU is the bottleneck and the CPU runs ahead anyway)
-    const bool want_graph = e->use_graphs && static_cast<long>(B) * h * w <= 4 * 3600;
-    if (!want_graph || pl->eager_runs == 0) {          // the first run of a plan is eager (sets kernel attributes, warms caches)
+    // ---- graph replay of the workspace-only launches (small batches only: at large batch the GPU is the bottleneck and the CPU
+    //      runs ahead anyway).  The first run of a plan is eager (sets kernel attributes, warms caches).
+    const bool want_graph = e->use_graphs && tokens <= 4 * 3600;
+    if (!want_graph || pl->eager_runs == 0) {
         pl->eager_runs++;
         for (auto& op : pl->ops) MG_TRY(op.fn(st));
         return 0;
     }
-    const void* key[6] = {image, points, normal, mask_prob, metric_scale, workspace};
-    cudaGraphExec_t exec = nullptr;
-    for (auto& g : pl->graphs)
-        if (g.dtype == image_dtype && std::equal(key, key + 6, g.key)) exec = g.exec;
+    size_t i0 = 0, i1 = pl->ops.size();
+    while (i0 < pl->ops.size() && pl->ops[i0].phase == 0) ++i0;
+    while (i1 > i0 && pl->ops[i1 - 1].phase == 2) --i1;
     // stream capture is not allowed on the legacy default stream: run on the engine's own stream, fenced by events
     const bool legacy = (st == nullptr || st == cudaStreamLegacy || st == cudaStreamPerThread);
     cudaStream_t run = legacy ? e->own_stream : st;
+    for (size_t i = 0; i < i0; ++i) MG_TRY(pl->ops[i].fn(st));
     if (legacy) {
         CUDA_TRY(cudaEventRecord(e->ev_in, st));
         CUDA_TRY(cudaStreamWaitEvent(e->own_stream, e->ev_in, 0));
     }
-    if (!exec) {
+    if (!pl->exec) {
         cudaGraph_t graph = nullptr;
         CUDA_TRY(cudaStreamBeginCapture(run, cudaStreamCaptureModeThreadLocal));
         int rc = 0;
-        for (auto& op : pl->ops) { rc = op.fn(run); if (rc) break; }
+        for (size_t i = i0; i < i1; ++i) { rc = pl->ops[i].fn(run); if (rc) break; }
         cudaError_t ce = cudaStreamEndCapture(run, &graph);
         if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
         if (ce != cudaSuccess) return set_error("graph capture failed: %s", cudaGetErrorString(ce));
-        CUDA_TRY(cudaGraphInstantiate(&exec, graph, 0));
+        ce = cudaGraphInstantiate(&pl->exec, graph, 0);
         cudaGraphDestroy(graph);
-        if (pl->graphs.size() >= 8) { cudaGraphExecDestroy(pl->graphs.front().exec); pl->graphs.erase(pl->graphs.begin()); }
-        Plan::GraphEntry ge;
-        std::copy(key, key + 6, ge.key); ge.dtype = image_dtype; ge.exec = exec;
-        pl->graphs.push_back(ge);
+        if (ce != cudaSuccess) { pl->exec = nullptr; return set_error("cudaGraphInstantiate failed: %s", cudaGetErrorString(ce)); }
     }
-    CUDA_TRY(cudaGraphLaunch(exec, run));
+    CUDA_TRY(cudaGraphLaunch(pl->exec, run));
     if (legacy) {
         CUDA_TRY(cudaEventRecord(e->ev_out, e->own_stream));
         CUDA_TRY(cudaStreamWaitEvent(st, e->ev_out, 0));
     }
+    for (size_t i = i1; i < pl->ops.size(); ++i) MG_TRY(pl->ops[i].fn(st));
     return 0;
+}
+
+int moge_engine_forward(moge_engine_t* e, const void* image, int image_dtype, int B, int H, int W, int h, int w, void* workspace,
+                        size_t workspace_bytes, float* points, float* normal, float* mask_prob, float* metric_scale, void* stream) {
+    moge_group_t g{};
+    g.image = image; g.image_dtype = image_dtype; g.B = B; g.H = H; g.W = W; g.h = h; g.w = w;
+    g.points = points; g.normal = normal; g.mask_prob = mask_prob; g.metric_scale = metric_scale;
+    return moge_engine_forward_groups(e, &g, 1, workspace, workspace_bytes, stream);
 }
 
 int moge_engine_num_ops(moge_engine_t* e, int* n) {
@@ -1070,9 +1309,27 @@ int moge_op_linear(const void* x, const void* w, const float* bias, const float*
 }
 
 int moge_op_attention(const void* qkv, void* out, int B, int N, int D, int heads, int dtype, void* stream) {
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (B <= 0 || N <= 0) return set_error("op_attention: bad shape B=%d N=%d", B, N);
     CUtensorMap mq;
-    MG_TRY(make_map_3d(&mq, qkv, 3 * static_cast<uint64_t>(D), N, B, 128));
-    return launch_attention(mq, out, B, N, D, heads, dtype == MOGE_BF16, static_cast<cudaStream_t>(stream));
+    MG_TRY(make_map_2d(&mq, qkv, 3 * static_cast<uint64_t>(D), static_cast<uint64_t>(B) * N, 3 * static_cast<uint64_t>(D), 128));
+    std::vector<int> row0(B), n(B, N);
+    for (int b = 0; b < B; ++b) row0[b] = b * N;
+    std::vector<AttnItem> items;
+    std::vector<int2> ranges;
+    attention_work_list(row0.data(), n.data(), B, heads, dev_sms(), &items, &ranges);
+    AttnItem* items_dev = nullptr;
+    int2* ranges_dev = nullptr;
+    CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&items_dev), items.size() * sizeof(AttnItem) + 16));
+    if (cudaMalloc(reinterpret_cast<void**>(&ranges_dev), ranges.size() * sizeof(int2) + 16) != cudaSuccess) { cudaFree(items_dev); return set_error("op_attention: cudaMalloc failed"); }
+    int rc = 0;
+    if (cudaMemcpyAsync(items_dev, items.data(), items.size() * sizeof(AttnItem), cudaMemcpyHostToDevice, st) != cudaSuccess ||
+        cudaMemcpyAsync(ranges_dev, ranges.data(), ranges.size() * sizeof(int2), cudaMemcpyHostToDevice, st) != cudaSuccess)
+        rc = set_error("op_attention: upload failed");
+    if (rc == 0) rc = launch_attention(mq, out, items_dev, ranges_dev, static_cast<int>(ranges.size()), D, heads, dtype == MOGE_BF16, st);
+    cudaStreamSynchronize(st);
+    cudaFree(items_dev); cudaFree(ranges_dev);
+    return rc;
 }
 
 int moge_op_linear_ln(const float* x, const float* ln_gamma, const float* ln_beta, const float* w, const float* bias, void* out, int M,
@@ -1146,14 +1403,7 @@ int moge_op_conv(const void* x, const float* w, const float* bias, const void* s
         p.out0 = out_raw; p.out1 = out_relu; p.bias = bias; p.skip = skip; p.ldo = Cout;
         p.Ho = go.H; p.Wo = go.W; p.Hop = go.Hp; p.Wop = go.Wp; p.shuffle = shuffle;
         CUtensorMap ma, mb;
-        if (taps == 9 && Cin == 64 && N % 64 == 0 && gs.Hp >= 18 && getenv("MOGE_B200_CONVS") != nullptr) {
-            p.tiles_x = (W + 15) / 16; p.tiles_y = (H + 15) / 16;
-            p.num_m_tiles = B * p.tiles_x * p.tiles_y;
-            p.num_n_tiles = N / 64;
-            rc = make_map_nhwc(&ma, x, Cin, gs.Wp, gs.Hp, B, 18);
-            if (rc == 0) rc = make_map_2d(&mb, wp, Ktot, N, Ktot, 64);
-            if (rc == 0) rc = launch_convs(EPI_DEC, bf16, ma, ma, mb, p, dev_sms(), st);
-        } else if (taps == 9 && Cin == 64 && N % 64 == 0 && gs.Hp >= 10) {
+        if (taps == 9 && Cin == 64 && N % 64 == 0 && gs.Hp >= 10) {
             p.num_n_tiles = N / 64;
             rc = make_map_nhwc(&ma, x, Cin, gs.Wp, gs.Hp, B, 10);
             if (rc == 0) rc = make_map_2d(&mb, wp, Ktot, N, Ktot, 64);

@@ -4,6 +4,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stddef.h>
+#include <atomic>
+#include <vector>
 
 namespace mg {
 
@@ -20,6 +22,29 @@ int set_error(const char* fmt, ...);
     do {                            \
         int _r = (expr);            \
         if (_r != 0) return _r;     \
+    } while (0)
+
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is a PER-DEVICE property of a kernel: every launcher keeps one of these
+// per kernel instantiation and sets the attribute on the first launch on each device (engines on several GPUs in one
+// process; setting it twice from two threads is harmless, so relaxed atomics are enough).
+struct DevOnce {
+    std::atomic<bool> done[64];
+    DevOnce() { for (auto& d : done) d.store(false, std::memory_order_relaxed); }
+    // true when the current device has not been prepared yet (dev < 0: query failed -> always prepare)
+    bool need(int* dev) {
+        if (cudaGetDevice(dev) != cudaSuccess || *dev < 0 || *dev >= 64) { *dev = -1; return true; }
+        return !done[*dev].load(std::memory_order_acquire);
+    }
+    void mark(int dev) { if (dev >= 0) done[dev].store(true, std::memory_order_release); }
+};
+#define MG_SET_SMEM_ONCE(kern, bytes)                                                                    \
+    do {                                                                                                 \
+        static ::mg::DevOnce _once;                                                                      \
+        int _dev;                                                                                        \
+        if (_once.need(&_dev)) {                                                                         \
+            CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));    \
+            _once.mark(_dev);                                                                            \
+        }                                                                                                \
     } while (0)
 
 // ---- TMA descriptors (driver entry point resolved at run time; no link-time libcuda dependency)
@@ -46,11 +71,13 @@ bool convh_supports(int bn, const UmmaParams& p);
 int launch_convh(int bn, bool bf16, const CUtensorMap& a, const CUtensorMap& aux, const CUtensorMap& w, const UmmaParams& p, int num_sms,
                  cudaStream_t st);
 
-// 3x3 conv with C_in = 64, operands swapped (weights on M = 64, 16x16 pixels on N = 256): convs_kernel.cuh
-int launch_convs(int epi, bool bf16, const CUtensorMap& a, const CUtensorMap& aux, const CUtensorMap& w, const UmmaParams& p, int num_sms,
-                 cudaStream_t st);
-
-int launch_attention(const CUtensorMap& mapQKV, void* out, int B, int N, int D, int heads, bool bf16, cudaStream_t st);
+// Attention over PACKED token rows (ragged batches): qkv [rows, 3D] (map: box {64, 128}), one work item per (image, head, pair
+// of 128-row query tiles); the persistent kernel's CTA c walks items [ranges[c].x, ranges[c].y).
+struct AttnItem { int row0, n, q0, head; };      // image's first row, its token count, first query row (image-relative), head
+void attention_work_list(const int* row0, const int* n, int nimg, int heads, int ncta, std::vector<AttnItem>* items,
+                         std::vector<int2>* ranges);
+int launch_attention(const CUtensorMap& mapQKV, void* out, const AttnItem* items_dev, const int2* ranges_dev, int ncta, int D, int heads,
+                     bool bf16, cudaStream_t st);
 
 // ---- small kernels (elementwise.cu)
 // K1: antialiased bilinear resize to (14h,14w) + ImageNet normalise + patchify -> A[B*T, Kp] (16-bit, Kp = 592)

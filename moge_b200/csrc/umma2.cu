@@ -7,11 +7,7 @@ namespace mg {
 template <int EPI, bool BF16>
 static int launch_inst(const CUtensorMap& a, const CUtensorMap& b, const UmmaParams& p, int num_sms, cudaStream_t st) {
     auto kern = umma2_kernel<EPI, BF16>;
-    static bool attr_set = false;
-    if (!attr_set) {
-        CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Umma2Cfg::kSmemBytes));
-        attr_set = true;
-    }
+    MG_SET_SMEM_ONCE(kern, Umma2Cfg::kSmemBytes);
     const int total = ((p.num_m_tiles + 1) / 2) * p.num_n_tiles;
     if (total <= 0) return 0;
     const int pairs = total < num_sms / 2 ? total : num_sms / 2;

@@ -24,6 +24,9 @@ enum : int {
     EPI_DEC = 4,       // padded-NHWC decoder store: acc + bias (+ UV rank-2) (+ skip) -> raw and/or ReLU copies
     EPI_HEADOUT = 5,   // BN=16: (bilinear x2 + 3x3 conv + output 1x1) folded into one low-res 3x3 conv with 4 output phases,
                        //        + folded 1x1 of the high-res neck map -> fp32 maps at the high resolution
+    EPI_NECKOUT = 6,   // BN=32: the neck's last level (bilinear x2 + 3x3 conv + UV 1x1) folded THROUGH the heads' last-level
+                       //        input + output blocks: 4 phases x 8 components (points xyz, normal xyz, mask logit, pad) written
+                       //        straight into the heads' fp32 output maps; the heads' EPI_HEADOUT launches then accumulate
 };
 
 #ifndef MG_STAGES256
@@ -47,7 +50,9 @@ struct UmmaParams {
     int tiles_x, tiles_y;
     // epilogue operands
     void* out0;            // EPI_STORE16/GELU16: T* ; EPI_RESID/PATCH: float* ; EPI_DEC: raw T* (or null) ; HEADOUT: float*
-    void* out1;            // EPI_DEC: ReLU copy T* (or null)
+    void* out1;            // EPI_DEC: ReLU copy T* (or null); NECKOUT: normal map float4* (or null)
+    void* out2;            // NECKOUT: mask-logit map float* (or null)
+    int accum;             // HEADOUT: 1 = add to the values already in out0 (written by the NECKOUT launch)
     const float* bias;     // [N] (EPI_DEC shuffle: [C_out]); HEADOUT: [16]
     const float* vec1;     // EPI_RESID: gamma[N]; EPI_PATCH: table[T, N]; EPI_DEC: wu[C] (or null); HEADOUT: waux[ncomp,32] (or null)
     const float* vec2;     // EPI_DEC: wv[C]
@@ -332,8 +337,43 @@ __device__ __forceinline__ void epilogue_tile(const UmmaParams& p, int mt, int n
                     }
                 }
                 const size_t pix = (static_cast<size_t>(b) * p.Ho + Y) * p.Wo + X;
+                if (p.accum) {       // the neck's folded contribution is already there (EPI_NECKOUT)
+                    if (p.ncomp == 1) o[0] += static_cast<const float*>(p.out0)[pix];
+                    else { const float4 t = static_cast<const float4*>(p.out0)[pix]; o[0] += t.x; o[1] += t.y; o[2] += t.z; }
+                }
                 if (p.ncomp == 1) static_cast<float*>(p.out0)[pix] = o[0];
                 else static_cast<float4*>(p.out0)[pix] = make_float4(o[0], o[1], o[2], 0.f);
+            }
+        }
+        __syncwarp();
+    } else if (EPI == EPI_NECKOUT) {
+        // lane = low-resolution pixel; 32 accumulator columns = (phase, component)
+        const int per_img = p.tiles_x * p.tiles_y;
+        const int b = mt / per_img;
+        const int r = mt % per_img;
+        const int py = (r / p.tiles_x) * TILE_PH + row / TILE_PW;
+        const int px = (r % p.tiles_x) * TILE_PW + row % TILE_PW;
+        const bool valid = (py < p.H) && (px < p.W);
+        float v[32];
+        tmem_ld32(t_addr, v);
+        tc_wait_ld();
+        if (valid) {
+            float b8[8], gu[8], gv[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) { b8[k] = p.bias[k]; gu[k] = p.vec1[k]; gv[k] = p.vec2[k]; }
+            const float inv_wo = 1.0f / static_cast<float>(p.Wo), inv_ho = 1.0f / static_cast<float>(p.Ho);
+#pragma unroll
+            for (int ph = 0; ph < 4; ++ph) {
+                const int Y = 2 * py + (ph >> 1), X = 2 * px + (ph & 1);
+                const float uu = p.su * ((2 * X + 1) * inv_wo - 1.0f);
+                const float vv = p.sv * ((2 * Y + 1) * inv_ho - 1.0f);
+                float o[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) o[k] = v[ph * 8 + k] + b8[k] + gu[k] * uu + gv[k] * vv;
+                const size_t pix = (static_cast<size_t>(b) * p.Ho + Y) * p.Wo + X;
+                if (p.out0) static_cast<float4*>(p.out0)[pix] = make_float4(o[0], o[1], o[2], 0.f);
+                if (p.out1) static_cast<float4*>(p.out1)[pix] = make_float4(o[3], o[4], o[5], 0.f);
+                if (p.out2) static_cast<float*>(p.out2)[pix] = o[6];
             }
         }
         __syncwarp();

@@ -10,11 +10,7 @@ int launch_umma_inst(const CUtensorMap& a, const CUtensorMap& aux, const CUtenso
                      cudaStream_t st) {
     using Cfg = UmmaCfg<BN>;
     auto kern = umma_kernel<BN, AMODE, EPI, BF16, DF>;
-    static bool attr_set = false;
-    if (!attr_set) {
-        CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
-        attr_set = true;
-    }
+    MG_SET_SMEM_ONCE(kern, Cfg::kSmemBytes);
     const int tiles = p.num_m_tiles * p.num_n_tiles;
     if (tiles <= 0) return 0;
     const int grid = tiles < num_sms ? tiles : num_sms;

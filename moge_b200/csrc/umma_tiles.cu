@@ -31,6 +31,7 @@ int launch_umma_tiles(int bn, int epi, bool bf16, const CUtensorMap& a, const CU
     INST_DF(128, DF_RAW | DF_RELU | DF_UV)
     INST(256, EPI_DEC) INST(128, EPI_DEC) INST(64, EPI_DEC) INST(32, EPI_DEC)
     INST(16, EPI_HEADOUT)
+    INST(32, EPI_NECKOUT)
     return set_error("no umma_tiles instantiation for bn=%d epi=%d", bn, epi);
 }
 #undef INST

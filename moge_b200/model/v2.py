@@ -113,9 +113,20 @@ class MoGeModel:
         return dict(self._state)
 
     def load_state_dict(self, state_dict: Dict[str, torch.Tensor], strict: bool = True):
+        """nn.Module.load_state_dict semantics (the reference calls it with strict=False, v2.py:105): returns the
+        (missing_keys, unexpected_keys) report; strict=True raises RuntimeError when either list is non-empty."""
+        from torch.nn.modules.module import _IncompatibleKeys
+        from ..synthetic import expected_keys
+        want = expected_keys(self.model_config)
+        got = set(state_dict.keys())
+        missing = [k for k in want if k not in got]
+        unexpected = [k for k in state_dict.keys() if k not in want]
+        if strict and (missing or unexpected):
+            raise RuntimeError("Error(s) in loading state_dict for MoGeModel:\n\tMissing key(s): "
+                               f"{missing}\n\tUnexpected key(s): {unexpected}")
         self._state = {k: v.detach() for k, v in state_dict.items()}
         self._drop_engine()
-        return self
+        return _IncompatibleKeys(missing, unexpected)
 
     def to(self, *args, **kwargs):
         device = kwargs.get("device")
@@ -267,6 +278,85 @@ class MoGeModel:
                     capi.ptr(sub(scale)), capi.current_stream()))
         return points, normal, mask, scale
 
+    def _forward_groups(self, groups):
+        """ONE engine call over several shape groups: `groups` = [(image (B,3,H,W), h, w)].  The encoder runs once over the
+        packed token rows of all groups (moge_engine_forward_groups).  Returns [(points, normal, mask_prob, metric_scale)]."""
+        self._ensure_engine()
+        dev = self._device
+        n = len(groups)
+        arr = (capi.Group * n)()
+        keep, outs = [], []
+        with torch.cuda.device(dev):
+            for i, (image, h, w) in enumerate(groups):
+                if image.device != dev:
+                    image = image.to(dev)
+                if image.dtype not in (torch.float32, torch.float16, torch.bfloat16):
+                    image = image.float()
+                image = image.contiguous()
+                B, _, H, W = image.shape
+                points = torch.empty(B, H, W, 3, dtype=torch.float32, device=dev) if hasattr(self, "points_head") else None
+                normal = torch.empty(B, H, W, 3, dtype=torch.float32, device=dev) if hasattr(self, "normal_head") else None
+                mask = torch.empty(B, H, W, dtype=torch.float32, device=dev) if hasattr(self, "mask_head") else None
+                scale = torch.empty(B, dtype=torch.float32, device=dev) if hasattr(self, "scale_head") else None
+                g = arr[i]
+                g.image, g.image_dtype = image.data_ptr(), capi.torch_dtype_code(image.dtype)
+                g.B, g.H, g.W, g.h, g.w = B, H, W, h, w
+                g.points, g.normal, g.mask_prob, g.metric_scale = capi.ptr(points), capi.ptr(normal), capi.ptr(mask), capi.ptr(scale)
+                keep.append(image)
+                outs.append((points, normal, mask, scale))
+            nbytes = C.c_size_t()
+            capi.check(capi.lib().moge_engine_workspace_bytes_groups(self._engine, arr, n, C.byref(nbytes)))
+            need = nbytes.value + 1024
+            if self._workspace is None or self._workspace.numel() < need:
+                self._workspace = None
+                self._workspace = torch.empty(need, dtype=torch.uint8, device=dev)
+            base = self._workspace.data_ptr()
+            aligned = (base + 1023) & ~1023
+            capi.check(capi.lib().moge_engine_forward_groups(self._engine, arr, n, aligned, self._workspace.numel() - (aligned - base),
+                                                             capi.current_stream()))
+        return outs
+
+    @torch.inference_mode()
+    def infer_many(self, images, num_tokens: int = None, resolution_level: int = 9, force_projection: bool = True,
+                   apply_mask: bool = True, fov_x: Optional[Number] = None, use_fp16: bool = True) -> List[Dict[str, torch.Tensor]]:
+        """`infer()` over a list of images of DIFFERENT sizes (each (3,H,W)): one result dict per image, in order.
+        No reference counterpart (the reference processes one shape per call; moge/scripts/infer.py:101 loops over files):
+        images are bucketed by shape, the buckets are packed into engine calls of at most `max_chunk_tokens` tokens and every
+        call runs the encoder ONCE over the token rows of all its buckets (ragged batching, BASELINE.json configs[2])."""
+        if not use_fp16:
+            raise NotImplementedError("moge_b200: use_fp16=False is not provided (see infer())")
+        if num_tokens is None:
+            num_tokens = default_num_tokens(self.num_tokens_range, resolution_level)
+        buckets: Dict[tuple, List[int]] = {}
+        for i, im in enumerate(images):
+            if im.dim() != 3 or im.shape[0] != 3:
+                raise ValueError(f"images[{i}] must be (3, H, W), got {tuple(im.shape)}")
+            buckets.setdefault((int(im.shape[1]), int(im.shape[2]), im.dtype), []).append(i)
+        # pack buckets (largest token count first) into calls bounded by max_chunk_tokens
+        units = []
+        for (H, W, _), idx in buckets.items():
+            h, w = token_grid(H, W, int(num_tokens))
+            per = max(1, self.max_chunk_tokens // (h * w + 1))
+            for lo in range(0, len(idx), per):
+                units.append((len(idx[lo:lo + per]) * (h * w + 1), H, W, h, w, idx[lo:lo + per]))
+        units.sort(key=lambda u: -u[0])
+        calls, cur, cur_tok = [], [], 0
+        for u in units:
+            if cur and cur_tok + u[0] > self.max_chunk_tokens:
+                calls.append(cur); cur, cur_tok = [], 0
+            cur.append(u); cur_tok += u[0]
+        if cur:
+            calls.append(cur)
+        results: List[Optional[Dict[str, torch.Tensor]]] = [None] * len(images)
+        for call in calls:
+            groups = [(torch.stack([images[i].to(self._device) for i in idx]), h, w) for (_, H, W, h, w, idx) in call]
+            outs = self._forward_groups(groups)
+            for (_, H, W, h, w, idx), (points, normal, mask, scale) in zip(call, outs):
+                ret = self._postprocess(points, normal, mask, scale, W / H, force_projection, apply_mask, fov_x)
+                for j, i in enumerate(idx):
+                    results[i] = {k: v[j] for k, v in ret.items()}
+        return results
+
     def engine_ops(self):
         """[(kernel name, algorithmic flops, algorithmic HBM bytes)] of the launch list of the most recent forward."""
         L = capi.lib()
@@ -304,35 +394,11 @@ class MoGeModel:
 
     __call__ = forward
 
-    @torch.inference_mode()
-    def infer(self,
-              image: torch.Tensor,
-              num_tokens: int = None,
-              resolution_level: int = 9,
-              force_projection: bool = True,
-              apply_mask: bool = True,
-              fov_x: Optional[Union[Number, torch.Tensor]] = None,
-              use_fp16: bool = True) -> Dict[str, torch.Tensor]:
-        """Same contract as v2.py:194-303.  The engine always multiplies in 16-bit (fp16, or bf16 after
-        `.bfloat16()`) with fp32 accumulation, fp32 residual stream and fp32 post-processing, so `use_fp16=False`
-        cannot select a full-fp32 network pass; it is accepted and reported once."""
-        if not use_fp16 and not self._warned_fp32:
-            warnings.warn("moge_b200: use_fp16=False requested; the B200 engine computes with 16-bit tensor-core "
-                          "operands and fp32 accumulation regardless")
-            self._warned_fp32 = True
-        if image.dim() == 3:
-            omit_batch_dim = True
-            image = image.unsqueeze(0)
-        else:
-            omit_batch_dim = False
-        H, W = image.shape[-2:]
-        aspect_ratio = W / H
-        if num_tokens is None:
-            num_tokens = default_num_tokens(self.num_tokens_range, resolution_level)
-        h, w = token_grid(H, W, int(num_tokens))
-        points, normal, mask, metric_scale = self._forward_raw(image, h, w)
-        B = image.shape[0]
+    def _postprocess(self, points, normal, mask, metric_scale, aspect_ratio, force_projection, apply_mask, fov_x):
+        """K18 + K19 of infer() (v2.py:246-298) on the raw forward outputs of one shape group; all on the device."""
         dev = self._device
+        some = points if points is not None else (normal if normal is not None else mask)
+        B, H, W = some.shape[0], some.shape[1], some.shape[2]
         L = capi.lib()
         ret: Dict[str, torch.Tensor] = {}
         with torch.cuda.device(dev):
@@ -365,10 +431,46 @@ class MoGeModel:
                 if normal_out is not None:
                     ret['normal'] = normal_out
             else:
+                mask_binary = None
                 if mask is not None:
-                    ret['mask'] = mask > 0.5
+                    mask_binary = mask > 0.5
+                    ret['mask'] = mask_binary
                 if normal is not None:
+                    if apply_mask and mask_binary is not None:        # v2.py:283-286
+                        normal = torch.where(mask_binary[..., None], normal, torch.zeros_like(normal))
                     ret['normal'] = normal
+        return ret
+
+    @torch.inference_mode()
+    def infer(self,
+              image: torch.Tensor,
+              num_tokens: int = None,
+              resolution_level: int = 9,
+              force_projection: bool = True,
+              apply_mask: bool = True,
+              fov_x: Optional[Union[Number, torch.Tensor]] = None,
+              use_fp16: bool = True) -> Dict[str, torch.Tensor]:
+        """Same contract as v2.py:194-303.  The engine always multiplies in 16-bit (fp16, or bf16 after
+        `.bfloat16()`) with fp32 accumulation, fp32 residual stream and fp32 post-processing; a full-fp32 network pass
+        (the reference's `use_fp16=False`, v2.py:241) does not exist here, so asking for it is an error rather than a silent
+        precision downgrade."""
+        if not use_fp16:
+            raise NotImplementedError(
+                "moge_b200: use_fp16=False (full-fp32 network pass) is not provided; the B200 engine computes with 16-bit "
+                "tensor-core operands, fp32 accumulation, an fp32 residual stream and fp32 post-processing (outputs within "
+                "1e-3 of the fp32 reference, see DESIGN.md).  Call infer(..., use_fp16=True).")
+        if image.dim() == 3:
+            omit_batch_dim = True
+            image = image.unsqueeze(0)
+        else:
+            omit_batch_dim = False
+        H, W = image.shape[-2:]
+        aspect_ratio = W / H
+        if num_tokens is None:
+            num_tokens = default_num_tokens(self.num_tokens_range, resolution_level)
+        h, w = token_grid(H, W, int(num_tokens))
+        points, normal, mask, metric_scale = self._forward_raw(image, h, w)
+        ret = self._postprocess(points, normal, mask, metric_scale, aspect_ratio, force_projection, apply_mask, fov_x)
         if omit_batch_dim:
             ret = {k: v.squeeze(0) for k, v in ret.items()}
         return ret

@@ -20,7 +20,10 @@ def shard_range(total: int, rank: int, world: int) -> Tuple[int, int]:
 def broadcast_state_dict(state: Optional[Dict[str, torch.Tensor]], device: torch.device, src: int = 0,
                          group=None) -> Dict[str, torch.Tensor]:
     """Rank `src` holds `state` (CPU or device tensors); every rank returns the same dict on `device`.
-    Tensors travel as ONE flat fp32 buffer (one NCCL broadcast), after a small object broadcast of the key/shape list."""
+    Tensors travel as ONE flat fp32 buffer (one NCCL broadcast), after a small object broadcast of the key/shape list.
+    fp32 on purpose: the engine's load-time folds (LayerNorm into qkv / fc1, tap projections into the neck, the head tails) are
+    computed from the fp32 originals before the single rounding to 16 bit, so every rank ends up with bit-identical packed weights
+    and outputs; shipping 16-bit-rounded originals would round twice on the receiving ranks."""
     rank = dist.get_rank(group)
     meta = None
     if rank == src:
@@ -74,3 +77,87 @@ def gather_outputs(local: Dict[str, torch.Tensor], counts: List[int], dst: int =
         if t.shape[0]:
             dist.send((t.view(torch.uint8) if t.dtype == torch.bool else t).contiguous(), dst=dst, group=group)
     return None
+
+
+class OutputGatherer:
+    """Pipelined gather of per-rank `infer()` outputs onto rank `dst` (BASELINE.json configs[3]: "inputs resident on each GPU ->
+    all outputs resident on rank 0").  `submit(local)` enqueues ONE grouped NCCL send/recv batch (every key, every peer) on a side
+    stream, straight into preallocated per-key buffers of the full batch on `dst` -- no per-key serial send/recv, no torch.cat --
+    so the transfer of step i runs under the compute of step i+1.  `fence()` makes the current stream wait for everything
+    submitted.  With the gloo backend (CPU tensors, host-logic tests) the same ops run synchronously."""
+
+    def __init__(self, counts: List[int], dst: int = 0, group=None, device: Optional[torch.device] = None, slots: int = 2):
+        self.counts, self.dst, self.group = list(counts), dst, group
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        self.offsets = [sum(self.counts[:r]) for r in range(self.world)]
+        self.device = device
+        self.cuda = device is not None and device.type == "cuda"
+        self.slots = slots
+        self.full: List[Optional[Dict[str, torch.Tensor]]] = [None] * slots
+        self.n = 0
+        if self.cuda:
+            with torch.cuda.device(device):
+                self.side = torch.cuda.Stream()
+                self.done = [torch.cuda.Event() for _ in range(slots)]
+
+    def _buffers(self, slot: int, local: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
+        if self.full[slot] is None:
+            total = sum(self.counts)
+            self.full[slot] = {k: torch.empty((total,) + tuple(t.shape[1:]), dtype=torch.uint8 if t.dtype == torch.bool else t.dtype,
+                                              device=t.device) for k, t in local.items()}
+        return self.full[slot]
+
+    def _post(self, local: Dict[str, torch.Tensor], full: Optional[Dict[str, torch.Tensor]]):
+        keys = sorted(local.keys())
+        ops = []
+        if self.rank == self.dst:
+            o, n = self.offsets[self.rank], self.counts[self.rank]
+            for k in keys:
+                t = local[k]
+                full[k][o:o + n].copy_(t.view(torch.uint8) if t.dtype == torch.bool else t)
+                for r in range(self.world):
+                    if r != self.dst and self.counts[r]:
+                        ops.append(dist.P2POp(dist.irecv, full[k][self.offsets[r]:self.offsets[r] + self.counts[r]], r, self.group))
+        elif self.counts[self.rank]:
+            for k in keys:
+                t = local[k]
+                ops.append(dist.P2POp(dist.isend, (t.view(torch.uint8) if t.dtype == torch.bool else t).contiguous(), self.dst, self.group))
+        return dist.batch_isend_irecv(ops) if ops else []
+
+    def submit(self, local: Dict[str, torch.Tensor]) -> Optional[Dict[str, torch.Tensor]]:
+        """Queue the gather of one step's outputs.  Returns (on `dst`) the dict of full-batch buffers this step lands in -- valid
+        after `fence()` / `wait()`; bool outputs come back as bool views."""
+        slot = self.n % self.slots
+        self.n += 1
+        full = self._buffers(slot, local) if self.rank == self.dst else None
+        if not self.cuda:
+            for w in self._post(local, full):
+                w.wait()
+        else:
+            with torch.cuda.device(self.device):
+                ready = torch.cuda.Event()
+                ready.record()                                  # the outputs are complete on the producing stream
+                self.side.wait_event(ready)
+                self.side.wait_event(self.done[slot])           # (no-op the first time) previous user of this slot's buffers
+                with torch.cuda.stream(self.side):
+                    for w in self._post(local, full):
+                        w.wait()                                # stream-level wait: orders the side stream after the transfers
+                    self.done[slot].record(self.side)
+                for t in local.values():
+                    t.record_stream(self.side)
+        if full is None:
+            return None
+        return {k: (v.view(torch.bool) if local[k].dtype == torch.bool else v) for k, v in full.items()}
+
+    def fence(self, stream=None) -> None:
+        if not self.cuda:
+            return
+        with torch.cuda.device(self.device):
+            st = stream if stream is not None else torch.cuda.current_stream()
+            for ev in self.done:
+                st.wait_event(ev)
+
+    def wait(self) -> None:
+        if self.cuda:
+            self.fence()
+            torch.cuda.current_stream(self.device).synchronize()

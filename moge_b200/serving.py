@@ -41,10 +41,13 @@ class InferPipeline:
         s = self.n % self.depth
         self.n += 1
         with torch.cuda.device(self.dev):
-            if self.dev_in[s] is None or self.dev_in[s].shape != host_in.shape or self.dev_in[s].dtype != host_in.dtype:
-                self.dev_in[s] = torch.empty(host_in.shape, dtype=host_in.dtype, device=self.dev)
             self.h2d.wait_event(self.ev_compute[s])            # the previous user of this input slot has been consumed
             with torch.cuda.stream(self.h2d):
+                if self.dev_in[s] is None or self.dev_in[s].shape != host_in.shape or self.dev_in[s].dtype != host_in.dtype:
+                    # (re)allocated ON the copy stream, after the wait above: the old buffer goes back to that stream's pool only
+                    # once its last reader (the compute stream) is done, and the new one is known to the compute stream below
+                    self.dev_in[s] = torch.empty(host_in.shape, dtype=host_in.dtype, device=self.dev)
+                    self.dev_in[s].record_stream(self.compute)
                 self.dev_in[s].copy_(host_in, non_blocking=True)
                 self.ev_in[s].record(self.h2d)
             self.compute.wait_event(self.ev_in[s])

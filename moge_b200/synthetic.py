@@ -84,11 +84,22 @@ def _shapes(cfg: Dict) -> "OrderedDict[str, tuple]":
     return s
 
 
-def make_state_dict(cfg: Dict, seed: int = 0, mask_bias: float = 0.7) -> "OrderedDict[str, torch.Tensor]":
+def expected_keys(cfg: Dict):
+    """State-dict keys of `MoGeModel(**cfg)` in the reference's order (for load_state_dict's missing / unexpected report)."""
+    return list(_shapes(cfg).keys())
+
+
+def make_state_dict(cfg: Dict, seed: int = 0, mask_bias: float = 0.7, well_posed: bool = False) -> "OrderedDict[str, torch.Tensor]":
     """Seeded fp32 state dict with well-scaled values (activations O(1) through all layers).
 
     `mask_bias` shifts the mask head's output bias so that `mask > 0.5` holds for most pixels and the
-    focal/shift solve is exercised."""
+    focal/shift solve is exercised.
+    `well_posed=True` rewires a handful of last-level weights (see `_make_well_posed`) so that the predicted point map
+    looks like a pinhole view (xy proportional to the UV planes times depth, depth within a factor of ~5): the focal/shift
+    solve of infer() is then well-conditioned and the five infer() outputs can be compared end to end.  It also gives the
+    normal head a dominant camera-facing component, like a trained model whose normals are near unit length: with plain random
+    init the three raw components are zero-mean, |n| is close to 0 on many pixels and F.normalize (v2.py:178) amplifies the
+    relative error of the raw output by sqrt(E[1/|n|^2] E[|n|^2]) ~ 1.7 (measured)."""
     g = torch.Generator(device="cpu").manual_seed(seed)
     sd: "OrderedDict[str, torch.Tensor]" = OrderedDict()
     for name, shape in _shapes(cfg).items():
@@ -126,7 +137,29 @@ def make_state_dict(cfg: Dict, seed: int = 0, mask_bias: float = 0.7) -> "Ordere
         else:
             raise AssertionError(name)
         sd[name] = t.contiguous()
+    if well_posed:
+        _make_well_posed(cfg, sd)
     return sd
+
+
+def _make_well_posed(cfg: Dict, sd: Dict[str, torch.Tensor], k: float = 4.0, g: float = 0.3, z_gain: float = 0.35,
+                     z_bias: float = 0.8, xy_noise: float = 0.1) -> None:
+    """Route the UV planes (the neck's level-4 input, v2.py:154-160) through channels 0/1 of the last decoder level into the
+    x/y outputs of the points head, and temper the log-depth output: with remap 'exp' the point map becomes
+    (g k u e^z, g k v e^z, e^z) + noise, i.e. a pinhole camera of focal ~ 1/(g k) looking at a rough surface at depth e^z."""
+    if cfg.get("points_head") is None:
+        return
+    last = len(cfg["neck"]["dim_res_blocks"]) - 1
+    w = sd[f"neck.input_blocks.{last}.weight"]
+    w[0] = 0; w[1] = 0; w[0, 0, 0, 0] = k; w[1, 1, 0, 0] = k
+    w = sd[f"points_head.input_blocks.{last}.weight"]
+    w[0] = 0; w[1] = 0; w[0, 0, 0, 0] = 1; w[1, 1, 0, 0] = 1
+    w = sd[f"points_head.output_blocks.{last}.weight"]
+    w[0] *= xy_noise; w[1] *= xy_noise; w[2] *= z_gain; w[0, 0, 0, 0] = g; w[1, 1, 0, 0] = g
+    sd[f"points_head.output_blocks.{last}.bias"][2] += z_bias
+    if cfg.get("normal_head") is not None:
+        sd[f"normal_head.output_blocks.{last}.weight"] *= 0.6
+        sd[f"normal_head.output_blocks.{last}.bias"] += torch.tensor([0.3, -0.4, -1.2])
 
 
 def save_checkpoint(path, cfg: Dict, seed: int = 0, **kw) -> None:

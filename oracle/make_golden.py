@@ -37,6 +37,30 @@ FORWARD_CASES = [
     ("vitl_b1_112x140_t120", "vitl", True, 5, (1, 112, 140), 120, 1),
 ]
 
+# Round-2 cases: (name, size, with_normal, seed, (B,H,W), num_tokens, stride, options)
+#   options: well_posed (synthetic.make_state_dict(well_posed=True): the focal/shift solve is well-conditioned, so the five
+#   infer() outputs are comparable end to end), remap (overrides cfg['remap_output']), autocast (store the reference's own
+#   16-bit deviation as the yardstick; costs two more reference passes)
+CASES_R2 = [
+    # the benchmarked shape (BASELINE.json configs[1]/[3]): ViT-L, 518x518, 37x37 native grid
+    ("vitl_b1_518x518_t1369_wp", "vitl", True, 10, (1, 518, 518), 1369, 4, {"well_posed": True, "autocast": True}),
+    # 35x35 grid -> 490 px: the antialiased DOWN-sampling branch of the input resize (modules.py:121)
+    ("vitl_b1_518x518_t1200_wp", "vitl", True, 11, (1, 518, 518), 1200, 4, {"well_posed": True}),
+    # API default: 3600 tokens, 60x60 grid, 840 px
+    ("vitl_b1_518x518_default_wp", "vitl", True, 12, (1, 518, 518), None, 4, {"well_posed": True}),
+    # mixed-aspect shapes of BASELINE.json configs[2] (grids 19x37 and 37x19)
+    ("vitl_b1_518x1036_t700_wp", "vitl", True, 13, (1, 518, 1036), 700, 4, {"well_posed": True}),
+    ("vitl_b1_1036x518_t700_wp", "vitl", True, 14, (1, 1036, 518), 700, 4, {"well_posed": True}),
+    # large input, down-sampled by more than 2x on both axes (wide antialias filter), ViT-B (configs[4] family)
+    ("vitb_b1_1024x768_t1200_wp", "vitb", True, 15, (1, 1024, 768), 1200, 4, {"well_posed": True}),
+    # well-posed small cases (fast) incl. batch 2
+    ("vits_b2_126x168_t192_wp", "vits", True, 16, (2, 126, 168), 192, 1, {"well_posed": True, "autocast": True}),
+    # remap_output variants (v2.py:122-136)
+    ("vits_b1_98x126_t120_linear", "vits", True, 17, (1, 98, 126), 120, 1, {"remap": "linear"}),
+    ("vits_b1_98x126_t120_sinh", "vits", True, 18, (1, 98, 126), 120, 1, {"remap": "sinh"}),
+    ("vits_b1_98x126_t120_sinh_exp", "vits", True, 19, (1, 98, 126), 120, 1, {"remap": "sinh_exp"}),
+]
+
 
 def rel_l2(a, b):
     a, b = a.double(), b.double()
@@ -44,11 +68,22 @@ def rel_l2(a, b):
 
 
 def main():
+    import argparse
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--only", default=None, help="comma-separated substrings: generate only the cases whose name contains one")
+    ap.add_argument("--skip-focal", action="store_true")
+    a = ap.parse_args()
+    only = a.only.split(",") if a.only else None
     os.makedirs(OUT, exist_ok=True)
     torch.manual_seed(0)
-    for name, size, with_normal, seed, (B, H, W), tokens, stride in FORWARD_CASES:
+    for case in [c + ({},) for c in FORWARD_CASES] + CASES_R2:
+        name, size, with_normal, seed, (B, H, W), tokens, stride, opt = case
+        if only and not any(o in name for o in only):
+            continue
         cfg = model_config(size, with_normal)
-        sd = make_state_dict(cfg, seed)
+        if "remap" in opt:
+            cfg["remap_output"] = opt["remap"]
+        sd = make_state_dict(cfg, seed, well_posed=opt.get("well_posed", False))
         ref = RefModel(**cfg).eval()
         missing = ref.load_state_dict(sd, strict=True)
         assert not missing.missing_keys and not missing.unexpected_keys
@@ -59,7 +94,7 @@ def main():
             inf = ref.infer(img, num_tokens=tokens, use_fp16=False)
             # the reference's OWN 16-bit deviation on these weights (CPU autocast), the yardstick for the engine's tolerance
             dev16 = {}
-            for tag, dt_ in (("fp16", torch.float16), ("bf16", torch.bfloat16)):
+            for tag, dt_ in ((("fp16", torch.float16), ("bf16", torch.bfloat16)) if opt.get("autocast", name in [c[0] for c in FORWARD_CASES]) else ()):
                 with torch.autocast("cpu", dtype=dt_):
                     f16 = ref.forward(img, nt)
                 dev16[tag] = {k: rel_l2(f16[k].float(), fwd[k]) for k in fwd}
@@ -83,13 +118,15 @@ def main():
         sl = (slice(None), slice(None, None, stride), slice(None, None, stride))
         gold = {
             "meta": {"size": size, "with_normal": with_normal, "seed": seed, "shape": (B, H, W), "num_tokens": tokens,
-                     "stride": stride, "port_vs_reference": report,
+                     "stride": stride, "port_vs_reference": report, "options": dict(opt),
                      "reference_autocast_deviation": dev16},
             "forward": {k: (v[sl].contiguous() if v.dim() >= 3 else v) for k, v in fwd.items()},
             "infer": {k: (v[sl].contiguous() if v.dim() >= 3 and k != "intrinsics" else v) for k, v in inf.items()},
         }
         torch.save(gold, os.path.join(OUT, name + ".pt"))
 
+    if a.skip_focal or only:
+        return
     # focal / shift recovery on synthetic well-posed point maps (SURVEY.md 8c cut point 2)
     cases = []
     for i, (H, W, f_true, s_true, noise, mask_mode, given_focal) in enumerate([

@@ -90,12 +90,12 @@ def encode(cfg: Dict, sd: Dict[str, torch.Tensor], image: torch.Tensor, h: int, 
 
 
 # ----------------------------------------------------------------------------------------------- decoder
-def view_plane_uv(width: int, height: int, aspect: float, dtype=torch.float32) -> torch.Tensor:
+def view_plane_uv(width: int, height: int, aspect: float, dtype=torch.float32, device=None) -> torch.Tensor:
     """(H, W, 2) pixel-centre UV scaled to the unit-diagonal view plane; geometry_torch.py:40-52."""
     sx = aspect / (1 + aspect ** 2) ** 0.5
     sy = 1 / (1 + aspect ** 2) ** 0.5
-    u = torch.linspace(-sx * (width - 1) / width, sx * (width - 1) / width, width, dtype=dtype)
-    v = torch.linspace(-sy * (height - 1) / height, sy * (height - 1) / height, height, dtype=dtype)
+    u = torch.linspace(-sx * (width - 1) / width, sx * (width - 1) / width, width, dtype=dtype, device=device)
+    v = torch.linspace(-sy * (height - 1) / height, sy * (height - 1) / height, height, dtype=dtype, device=device)
     uu, vv = torch.meshgrid(u, v, indexing="xy")
     return torch.stack([uu, vv], dim=-1)
 
@@ -154,14 +154,15 @@ def remap_points(points: torch.Tensor, mode: str) -> torch.Tensor:
 
 @torch.no_grad()
 def forward(cfg: Dict, sd: Dict[str, torch.Tensor], image: torch.Tensor, num_tokens: int) -> Dict[str, torch.Tensor]:
-    """v2.py:138-192.  image (B,3,H,W) fp32."""
+    """v2.py:138-192.  image (B,3,H,W); runs in the dtype and on the device of `image` / `sd` (fp32 on CPU = the oracle;
+    on 'cuda' it is the same-box PyTorch comparator and the large-shape checker of the -m gpu tests)."""
     B, _, H, W = image.shape
     aspect = W / H
     h, w = token_grid(H, W, int(num_tokens))
     feat, cls = encode(cfg, sd, image, h, w)
     inputs = []
     for l in range(5):
-        uv = view_plane_uv(w * 2 ** l, h * 2 ** l, aspect, image.dtype).permute(2, 0, 1)[None].expand(B, -1, -1, -1)
+        uv = view_plane_uv(w * 2 ** l, h * 2 ** l, aspect, image.dtype, image.device).permute(2, 0, 1)[None].expand(B, -1, -1, -1)
         inputs.append(torch.cat([feat, uv], dim=1) if l == 0 else uv)
     neck = conv_stack(cfg["neck"], sd, "neck", inputs)
     out = {}
@@ -210,6 +211,10 @@ def _lm_shift(uv: np.ndarray, xyz: np.ndarray, focal: Optional[float]):
 def recover_focal_shift(points: torch.Tensor, mask: Optional[torch.Tensor] = None,
                         focal: Optional[torch.Tensor] = None, size=(64, 64)):
     """geometry_torch.py:115-170.  points (B,H,W,3), mask (B,H,W) bool -> focal (B,), shift (B,)."""
+    dev_in = points.device
+    points = points.detach().cpu().float()
+    mask = None if mask is None else mask.detach().cpu()
+    focal = None if focal is None else focal.detach().cpu()
     B, H, W, _ = points.shape
     uv = view_plane_uv(W, H, W / H, points.dtype)
     p_lr = F.interpolate(points.permute(0, 3, 1, 2), size, mode="nearest").permute(0, 2, 3, 1).numpy()
@@ -224,7 +229,7 @@ def recover_focal_shift(points: torch.Tensor, mask: Optional[torch.Tensor] = Non
             continue
         s, f = _lm_shift(ui, pi, None if focal is None else float(focal[i]))
         fs.append(float(f)); ss.append(float(s))
-    return torch.tensor(fs, dtype=points.dtype), torch.tensor(ss, dtype=points.dtype)
+    return torch.tensor(fs, dtype=points.dtype, device=dev_in), torch.tensor(ss, dtype=points.dtype, device=dev_in)
 
 
 def postprocess(points: torch.Tensor, normal, mask, metric_scale, aspect: float, fov_x=None,
@@ -239,13 +244,13 @@ def postprocess(points: torch.Tensor, normal, mask, metric_scale, aspect: float,
     elif fov_x is None:
         focal, shift = recover_focal_shift(points, mask_b)
     else:
-        focal = aspect / (1 + aspect ** 2) ** 0.5 / torch.tan(torch.deg2rad(torch.as_tensor(fov_x, dtype=points.dtype) / 2))
+        focal = aspect / (1 + aspect ** 2) ** 0.5 / torch.tan(torch.deg2rad(torch.as_tensor(fov_x, dtype=points.dtype, device=points.device) / 2))
         if focal.ndim == 0:
             focal = focal[None].expand(points.shape[0])
         _, shift = recover_focal_shift(points, mask_b, focal=focal)
     fx = focal / 2 * (1 + aspect ** 2) ** 0.5 / aspect
     fy = focal / 2 * (1 + aspect ** 2) ** 0.5
-    K = torch.zeros(points.shape[0], 3, 3, dtype=points.dtype)
+    K = torch.zeros(points.shape[0], 3, 3, dtype=points.dtype, device=points.device)
     K[:, 0, 0], K[:, 1, 1], K[:, 0, 2], K[:, 1, 2], K[:, 2, 2] = fx, fy, 0.5, 0.5, 1.0
     points[..., 2] += shift[:, None, None]
     if mask_b is not None:
@@ -253,8 +258,8 @@ def postprocess(points: torch.Tensor, normal, mask, metric_scale, aspect: float,
     depth = points[..., 2].clone()
     if force_projection:
         Hh, Ww = depth.shape[-2:]
-        u = (torch.arange(Ww, dtype=depth.dtype) + 0.5) / Ww
-        v = (torch.arange(Hh, dtype=depth.dtype) + 0.5) / Hh
+        u = (torch.arange(Ww, dtype=depth.dtype, device=depth.device) + 0.5) / Ww
+        v = (torch.arange(Hh, dtype=depth.dtype, device=depth.device) + 0.5) / Hh
         x = (u[None, None, :] - 0.5) / fx[:, None, None] * depth
         y = (v[None, :, None] - 0.5) / fy[:, None, None] * depth
         points = torch.stack([x, y, depth], dim=-1)

@@ -17,11 +17,33 @@ DEV = "cuda"
 _models = {}
 
 
-def get_model(size, with_normal, seed, dtype=torch.float16):
-    key = (size, with_normal, seed, dtype)
+# Tolerances of forward(), fp16 engine vs the reference's fp32 outputs, rel-L2 per output:
+#   * 1e-3 flat (the north-star figure) on points / mask / metric_scale / normal for checkpoints whose normal head behaves like a
+#     trained one (near-unit raw normals: the `well_posed` synthetic checkpoints -- every benchmark-shape case);
+#   * plain random-init checkpoints: `normal` 2e-3.  Their raw normal components are zero-mean, |n| is close to 0 on many pixels
+#     and F.normalize (v2.py:178) amplifies the relative error of the raw head output by sqrt(E[1/|n|^2] E[|n|^2]) ~ 1.7
+#     (profiles/r2_error_attribution.json); the reference's own fp16 autocast mode shows 1.1e-3 ... 1.9e-3 on the same weights;
+#   * remap 'sinh' (v2.py:126): sinh multiplies the relative error of a logit x by x coth(x) >= 1: points 1.5e-3.
+FWD_TOL = {"points": 1e-3, "mask": 1e-3, "metric_scale": 1e-3, "normal": 1e-3}
+BF16_TOL = {"points": 1e-2, "mask": 1e-2, "metric_scale": 1e-2, "normal": 1.5e-2}
+
+
+def fwd_tol(well_posed, remap=None, tag="fp16"):
+    tol = dict(FWD_TOL if tag == "fp16" else BF16_TOL)
+    if tag == "fp16" and not well_posed:
+        tol["normal"] = 2e-3
+    if tag == "fp16" and remap == "sinh":
+        tol["points"] = 1.5e-3
+    return tol
+
+
+def get_model(size, with_normal, seed, dtype=torch.float16, well_posed=False, remap=None):
+    key = (size, with_normal, seed, dtype, well_posed, remap)
     if key not in _models:
         cfg = model_config(size, with_normal)
-        sd = make_state_dict(cfg, seed)
+        if remap is not None:
+            cfg["remap_output"] = remap
+        sd = make_state_dict(cfg, seed, well_posed=well_posed)
         m = MoGeModel(**cfg)
         m.load_state_dict(sd)
         m = m.to(DEV).eval()
@@ -33,12 +55,14 @@ def get_model(size, with_normal, seed, dtype=torch.float16):
 
 
 def tolerances(meta, tag):
-    """Per-output tolerance: the north-star 1e-3 (1e-2 for bf16), or -- where the reference's OWN autocast path on the
-    same weights (measured on CPU by oracle/make_golden.py, stored in the golden) deviates more than that from its
-    fp32 result -- 1.1x that deviation: the engine must be at least as accurate as the reference's 16-bit mode."""
-    base = 1e-3 if tag == "fp16" else 1e-2
+    """Flat per-output tolerances (FWD_TOL / BF16_TOL).  The golden also stores the reference's OWN autocast deviation on the
+    same weights (CPU autocast, oracle/make_golden.py); it is printed next to the engine's as a yardstick, not used as slack."""
+    opt = meta.get("options", {})
+    tol = fwd_tol(opt.get("well_posed", False), opt.get("remap"), tag)
     dev = meta.get("reference_autocast_deviation", {}).get(tag, {})
-    return {k: max(base, 1.1 * v) for k, v in dev.items()}, base
+    if dev:
+        print("reference's own", tag, "autocast deviation:", {k: f"{v:.2e}" for k, v in dev.items()})
+    return tol, 1e-3 if tag == "fp16" else 1e-2
 
 
 def check_forward(out, ref, tol, s=1, tols=None):
@@ -124,7 +148,7 @@ def test_forward_and_infer_match_reference_golden(name, golden_dir):
             rep2[k] = rel_l2(inf[k].cpu()[:, ::s, ::s][b2], ginf[k][b2])
     print("infer vs reference golden rel-L2:", {k: f"{v:.2e}" for k, v in rep2.items()}, "mask agreement", float(agree))
     if "normal" in rep2:
-        assert rep2["normal"] < tols.get("normal", base) * 1.5
+        assert rep2["normal"] < tols["normal"] * 1.5          # masked subset of the forward normal (+ mask-boundary pixels)
     if well_posed:
         assert rep2["intrinsics"] < 0.05, rep2
 
@@ -179,7 +203,7 @@ def test_forward_matches_oracle_port_fresh_shape():
     ref = moge_port.forward(cfg, sd, img, 260)
     out = model.forward(img.to(DEV), 260)
     torch.cuda.synchronize()
-    check_forward(out, ref, 2e-3)        # no stored autocast yardstick for this shape: 2e-3 (parity)
+    check_forward(out, ref, 1e-3, 1, fwd_tol(False))
 
 
 def test_batch_invariance_and_squeeze():
@@ -317,7 +341,251 @@ def test_missing_weight_is_reported():
     sd = make_state_dict(cfg, 0)
     sd.pop("neck.res_blocks.2.1.layers.5.weight")
     m = MoGeModel(**cfg)
-    m.load_state_dict(sd)
+    with pytest.raises(RuntimeError, match="neck.res_blocks.2.1.layers.5.weight"):
+        m.load_state_dict(sd)                                  # strict=True: reported at load time, like nn.Module
+    rep = m.load_state_dict(sd, strict=False)
+    assert rep.missing_keys == ["neck.res_blocks.2.1.layers.5.weight"] and rep.unexpected_keys == []
     m = m.to(DEV)
     with pytest.raises(capi.MogeError, match="missing weight 'neck.res_blocks.2.1.layers.5.weight'"):
         m.forward(synthetic_images(1, 70, 98, 3).to(DEV), 100)
+
+
+# ------------------------------------------------------------------------------------------------ round 2: benchmark shapes
+R2_CASES = ["vitl_b1_518x518_t1369_wp", "vitl_b1_518x518_t1200_wp", "vitl_b1_518x518_default_wp", "vitl_b1_518x1036_t700_wp",
+            "vitl_b1_1036x518_t700_wp", "vitb_b1_1024x768_t1200_wp", "vits_b2_126x168_t192_wp", "vits_b1_98x126_t120_linear",
+            "vits_b1_98x126_t120_sinh", "vits_b1_98x126_t120_sinh_exp"]
+
+
+@pytest.mark.parametrize("name", R2_CASES)
+def test_benchmark_shapes_match_reference_golden(name, golden_dir):
+    """forward() AND the five infer() outputs against goldens of the unmodified reference (fp32, CPU) on the shapes the bench
+    and BASELINE.json name: ViT-L 518x518 at the native 37x37 grid (the benchmarked shape), 35x35 (antialiased DOWN-sampling of
+    the input), the API-default 60x60, the 2:1 / 1:2 mixed-aspect shapes, a 1024x768 ViT-B input, and the linear / sinh /
+    sinh_exp remaps.  `_wp` cases use the well-posed synthetic checkpoint (synthetic.make_state_dict(well_posed=True)), so the
+    focal/shift solve is well-conditioned and depth / points / intrinsics of infer() are asserted end to end."""
+    gold = torch.load(os.path.join(golden_dir, name + ".pt"), weights_only=False)
+    meta = gold["meta"]
+    opt = meta.get("options", {})
+    model, cfg, sd = get_model(meta["size"], meta["with_normal"], meta["seed"], well_posed=opt.get("well_posed", False),
+                               remap=opt.get("remap"))
+    B, H, W = meta["shape"]
+    img = synthetic_images(B, H, W, meta["seed"]).to(DEV)
+    nt = meta["num_tokens"] or default_num_tokens(cfg["num_tokens_range"])
+    s = meta["stride"]
+    out = model.forward(img, nt)
+    torch.cuda.synchronize()
+    assert set(out.keys()) == set(gold["forward"].keys())
+    tols, base = tolerances(meta, "fp16")
+    check_forward(out, gold["forward"], base, s, tols)
+    inf = model.infer(img, num_tokens=meta["num_tokens"])
+    torch.cuda.synchronize()
+    ginf = gold["infer"]
+    assert set(inf.keys()) == set(ginf.keys())
+    m_got = inf["mask"].cpu()[:, ::s, ::s]
+    agree = float((m_got == ginf["mask"]).float().mean())
+    both = m_got & ginf["mask"]
+    rep = {"intrinsics": rel_l2(inf["intrinsics"], ginf["intrinsics"])}
+    for k in ("points", "depth", "normal"):
+        if k in ginf:
+            rep[k] = rel_l2(inf[k].cpu()[:, ::s, ::s][both], ginf[k][both])
+    print("infer vs reference golden rel-L2:", {k: f"{v:.2e}" for k, v in rep.items()}, "mask agreement", agree)
+    assert agree > 0.997, agree
+    assert rep["normal"] < 1.5 * tols["normal"]
+    if opt.get("well_posed"):
+        # well-conditioned solve: the 1e-3 forward deviation is not amplified (SURVEY.md 8c cut point 1 + 3 chained)
+        assert rep["intrinsics"] < 1e-3, rep
+        assert rep["depth"] < 1.5e-3 and rep["points"] < 1.5e-3, rep
+
+
+def _gpu_oracle(cfg, sd, img, nt):
+    """The oracle port in fp32 on the GPU (TF32 off): the checker for shapes too large for the CPU suite.  It is itself pinned
+    against the CPU reference golden by test_gpu_oracle_is_pinned_to_the_reference_golden."""
+    old = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        sdd = {k: v.to(DEV) for k, v in sd.items()}
+        ref = {}
+        for lo in range(0, img.shape[0], 2):          # two images at a time: bounded fp32 activation memory
+            r = moge_port.forward(cfg, sdd, img[lo:lo + 2].to(DEV).float(), nt)
+            for k, v in r.items():
+                ref.setdefault(k, []).append(v.cpu())
+        return {k: torch.cat(v) for k, v in ref.items()}
+    finally:
+        torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = old
+
+
+def test_gpu_oracle_is_pinned_to_the_reference_golden(golden_dir):
+    gold = torch.load(os.path.join(golden_dir, "vitl_b1_518x518_t1369_wp.pt"), weights_only=False)
+    meta = gold["meta"]
+    cfg = model_config("vitl", True)
+    sd = make_state_dict(cfg, meta["seed"], well_posed=True)
+    img = synthetic_images(1, 518, 518, meta["seed"])
+    ref = _gpu_oracle(cfg, sd, img, 1369)
+    s = meta["stride"]
+    for k, g in gold["forward"].items():
+        got = ref[k][:, ::s, ::s] if ref[k].dim() >= 3 else ref[k]
+        e = rel_l2(got, g)
+        print("gpu oracle vs reference golden", k, f"{e:.2e}")
+        assert e < 5e-5, (k, e)
+
+
+def test_batched_benchmark_shape_matches_gpu_oracle():
+    """The benchmarked configuration, batched: ViT-L, 518x518, 37x37 grid, B = 8 -> the 2-CTA GEMMs with LayerNorm-statistics
+    producers, convh<256>, conv64 at 296x296, N = 1370 attention in 24 stacked blocks all run inside ONE checked forward; then
+    the same batch through transparent chunking (3 + 3 + 2 images: plan switch + ragged tail at the real workspace size)."""
+    model, cfg, sd = get_model("vitl", True, 10, well_posed=True)
+    img = synthetic_images(8, 518, 518, 40)
+    ref = _gpu_oracle(cfg, sd, img, 1369)
+    out = model.forward(img.to(DEV), 1369)
+    torch.cuda.synchronize()
+    names = [n for n, _, _ in model.engine_ops()]
+    assert any(n.startswith("gemm.qkv") for n in names)
+    check_forward(out, ref, 1e-3, 1, FWD_TOL)
+    for b in range(8):                        # per image as well: no image may hide behind the batch norm
+        for k in ("points", "mask"):
+            e = rel_l2(out[k][b], ref[k][b])
+            assert e < FWD_TOL[k] * 1.2, (b, k, e)
+    old = model.max_chunk_tokens
+    try:
+        model.max_chunk_tokens = 3 * 1370 + 7
+        chunked = model.forward(img.to(DEV), 1369)
+        torch.cuda.synchronize()
+    finally:
+        model.max_chunk_tokens = old
+    check_forward(chunked, ref, 1e-3, 1, FWD_TOL)
+
+
+def test_vitl_bf16_matches_gpu_oracle():
+    model, cfg, sd = get_model("vitl", True, 10, torch.bfloat16, well_posed=True)
+    img = synthetic_images(2, 518, 518, 41)
+    ref = _gpu_oracle(cfg, sd, img, 1369)
+    out = model.forward(img.to(DEV), 1369)
+    torch.cuda.synchronize()
+    check_forward(out, ref, 1e-2, 1, BF16_TOL)
+
+
+# ------------------------------------------------------------------------------------------------ round 2: ragged batches, plans, graphs
+def test_infer_many_mixed_shapes_matches_per_image_infer():
+    """Mixed-aspect batch (BASELINE.json configs[2] shapes, scaled down): ONE engine call packs the token rows of every shape
+    group (encoder linears over the concatenated rows, attention over a ragged work list); each image must come out as if it
+    had been inferred alone."""
+    model, cfg, sd = get_model("vits", True, 16, well_posed=True)
+    shapes = [(98, 196), (126, 168), (140, 140), (168, 126), (196, 98), (126, 168), (98, 196), (140, 140), (140, 140)]
+    imgs = [synthetic_images(1, H, W, 60 + i)[0].to(DEV) for i, (H, W) in enumerate(shapes)]
+    many = model.infer_many(imgs, num_tokens=130)
+    torch.cuda.synchronize()
+    names = [n for n, _, _ in model.engine_ops()]
+    assert sum(n.startswith("attention") for n in names) == 12            # ONE attention launch per block for all five shapes
+    assert sum(n.startswith("preprocess") for n in names) == 5
+    assert len(many) == len(imgs)
+    for i, im in enumerate(imgs):
+        one = model.infer(im, num_tokens=130)
+        torch.cuda.synchronize()
+        assert set(one.keys()) == set(many[i].keys())
+        assert torch.equal(one["mask"], many[i]["mask"]), i
+        m = one["mask"]
+        for k in ("depth", "points", "normal"):
+            e = rel_l2(many[i][k][m], one[k][m])
+            assert e < 1e-5, (i, k, e)
+        assert rel_l2(many[i]["intrinsics"], one["intrinsics"]) < 1e-5
+
+
+def test_infer_many_chunks_large_sets():
+    model, cfg, sd = get_model("vits", True, 16, well_posed=True)
+    imgs = [synthetic_images(1, 70 + 14 * (i % 3), 98, 80 + i)[0].to(DEV) for i in range(7)]
+    ref = [model.infer(im, num_tokens=60) for im in imgs]
+    old = model.max_chunk_tokens
+    try:
+        model.max_chunk_tokens = 3 * 61          # forces several engine calls with mixed groups
+        many = model.infer_many(imgs, num_tokens=60)
+    finally:
+        model.max_chunk_tokens = old
+    torch.cuda.synchronize()
+    for a, b in zip(ref, many):
+        assert torch.equal(a["mask"], b["mask"])
+        assert rel_l2(b["depth"][a["mask"]], a["depth"][a["mask"]]) < 1e-5
+
+
+def test_plan_cache_is_bounded_and_frees_device_memory():
+    """A serving process fed arbitrary resolutions: every new shape builds a plan (pos table, work list); old plans are evicted
+    (LRU, 16) and their device buffers freed -- device memory must not grow with the number of distinct shapes seen."""
+    model, cfg, sd = get_model("vits", True, 1)
+    sizes = [(56 + 14 * (i % 6), 56 + 14 * (i // 6)) for i in range(36)]
+    model.infer(synthetic_images(1, 140, 140, 0).to(DEV), num_tokens=100)          # workspace for the largest shape first
+    torch.cuda.synchronize()
+
+    def sweep():
+        for i, (H, W) in enumerate(sizes):
+            out = model.infer(synthetic_images(1, H, W, i).to(DEV), num_tokens=(H // 14) * (W // 14))
+            assert torch.isfinite(out["depth"][out["mask"]]).all()
+        torch.cuda.synchronize()
+
+    sweep()
+    free0 = torch.cuda.mem_get_info()[0]
+    for _ in range(3):
+        sweep()
+    free1 = torch.cuda.mem_get_info()[0]
+    assert free0 - free1 < 8 << 20, (free0, free1)
+    first = model.infer(synthetic_images(1, 56, 56, 0).to(DEV), num_tokens=16)      # an evicted shape is simply rebuilt
+    torch.cuda.synchronize()
+    assert torch.isfinite(first["depth"][first["mask"]]).all()
+
+
+def test_graph_replay_with_fresh_output_tensors():
+    """Batch-1 calls replay ONE CUDA graph of the workspace-only launches; the caller-bound input / output kernels run eagerly
+    around it, so keeping earlier results alive (fresh output addresses on every call) neither re-captures nor corrupts."""
+    model, cfg, sd = get_model("vits", True, 1)
+    imgs = [synthetic_images(1, 98, 126, 200 + i).to(DEV) for i in range(6)]
+    kept = [model.infer(im, num_tokens=63) for im in imgs]                 # results kept alive -> distinct output tensors
+    torch.cuda.synchronize()
+    again = [model.infer(im, num_tokens=63) for im in imgs]
+    torch.cuda.synchronize()
+    ptrs = {o["points"].data_ptr() for o in kept + again}
+    assert len(ptrs) == 12
+    for a, b in zip(kept, again):
+        for k in a:
+            assert torch.equal(a[k], b[k]), k
+    assert not torch.equal(kept[0]["depth"], kept[1]["depth"])
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
+def test_two_engines_on_two_devices_in_one_process():
+    cfg = model_config("vits", True)
+    sd = make_state_dict(cfg, 2)
+    img = synthetic_images(2, 98, 126, 5)
+    outs = []
+    for d in (0, 1):
+        m = MoGeModel(**cfg)
+        m.load_state_dict(sd)
+        m = m.to(f"cuda:{d}").eval()
+        o = m.infer(img.to(f"cuda:{d}"), num_tokens=63)
+        torch.cuda.synchronize(d)
+        outs.append({k: v.cpu() for k, v in o.items()})
+        assert o["points"].device.index == d
+    for k in outs[0]:
+        assert torch.equal(outs[0][k], outs[1][k]), k
+
+
+def test_neck_fold_matches_unfolded_decoder(monkeypatch):
+    """Default: the neck's last level is folded through the heads' last input / output blocks (EPI_NECKOUT, no 32-channel map at
+    the 16x grid).  MOGE_B200_NECKFOLD=0 keeps the map and the per-head mat-vec; same outputs up to 16-bit rounding noise."""
+    cfg = model_config("vitb", True)
+    sd = make_state_dict(cfg, 3)
+    img = synthetic_images(2, 112, 140, 77).to(DEV)
+
+    def run():
+        m = MoGeModel(**cfg)
+        m.load_state_dict(sd)
+        m = m.to(DEV).eval()
+        out = m.forward(img, 120)
+        torch.cuda.synchronize()
+        return {k: v.float().cpu() for k, v in out.items()}, [n for n, _, _ in m.engine_ops()]
+
+    monkeypatch.delenv("MOGE_B200_NECKFOLD", raising=False)
+    fold, names_fold = run()
+    monkeypatch.setenv("MOGE_B200_NECKFOLD", "0")
+    sep, names_sep = run()
+    assert any("neckout" in n for n in names_fold) and not any("neckout" in n for n in names_sep)
+    for k in sep:
+        assert rel_l2(fold[k], sep[k]) < 1.5e-3, (k, rel_l2(fold[k], sep[k]))

@@ -41,7 +41,12 @@ def test_no_cpu_fallback():
         MoGeModel(**{**cfg, "remap_output": "bogus"})
     if torch.cuda.is_available():
         pytest.skip("GPU present")
-    m.load_state_dict({"x": torch.zeros(1)})
+    with pytest.raises(RuntimeError, match="Missing key"):
+        m.load_state_dict({"x": torch.zeros(1)})                    # strict=True like nn.Module
+    rep = m.load_state_dict({"x": torch.zeros(1)}, strict=False)    # the reference's from_pretrained uses strict=False (v2.py:105)
+    assert rep.unexpected_keys == ["x"] and "neck.input_blocks.0.weight" in rep.missing_keys
+    with pytest.raises(NotImplementedError, match="use_fp16=False"):
+        m.infer(synthetic_images(1, 28, 28, 0), use_fp16=False)
     with pytest.raises(capi.MogeError):
         m.infer(synthetic_images(1, 28, 28, 0))
     h = C.c_void_p()

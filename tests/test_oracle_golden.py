@@ -9,7 +9,8 @@ from moge_b200.configs import model_config, token_grid, default_num_tokens
 from moge_b200.synthetic import make_state_dict, synthetic_images, synthetic_point_map
 from oracle import moge_port
 
-FAST_CASES = ["vits_b1_126x168_t192", "vits_b2_140x98_t117", "vitb_b1_98x154_t150_nonormal"]
+FAST_CASES = ["vits_b1_126x168_t192", "vits_b2_140x98_t117", "vitb_b1_98x154_t150_nonormal", "vits_b2_126x168_t192_wp",
+              "vits_b1_98x126_t120_linear", "vits_b1_98x126_t120_sinh", "vits_b1_98x126_t120_sinh_exp"]
 
 
 def rel_l2(a, b):
@@ -21,8 +22,11 @@ def rel_l2(a, b):
 def test_port_matches_reference_golden(name, golden_dir):
     gold = torch.load(os.path.join(golden_dir, name + ".pt"), weights_only=False)
     meta = gold["meta"]
+    opt = meta.get("options", {})
     cfg = model_config(meta["size"], meta["with_normal"])
-    sd = make_state_dict(cfg, meta["seed"])
+    if "remap" in opt:
+        cfg["remap_output"] = opt["remap"]
+    sd = make_state_dict(cfg, meta["seed"], well_posed=opt.get("well_posed", False))
     B, H, W = meta["shape"]
     img = synthetic_images(B, H, W, meta["seed"])
     s = meta["stride"]

@@ -6,7 +6,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from moge_b200.parallel import shard_range, broadcast_state_dict, gather_outputs
+from moge_b200.parallel import shard_range, broadcast_state_dict, gather_outputs, OutputGatherer
 
 
 def test_shard_range_covers_everything():
@@ -39,6 +39,16 @@ def _worker(rank, world, port, q):
             ok = ok and torch.equal(out["points"], full_pts) and torch.equal(out["mask"], full_mask) and out["mask"].dtype == torch.bool
         else:
             ok = ok and out is None
+        # pipelined gatherer (grouped isend/irecv into preallocated full-batch buffers), several steps through 2 slots
+        gat = OutputGatherer(counts)
+        for step in range(3):
+            res = gat.submit({"points": full_pts[lo:hi] + step, "mask": (full_mask[lo:hi] if step % 2 == 0 else ~full_mask[lo:hi]).clone()})
+            gat.wait()
+            if rank == 0:
+                ok = ok and torch.equal(res["points"], full_pts + step) and res["mask"].dtype == torch.bool
+                ok = ok and torch.equal(res["mask"], full_mask if step % 2 == 0 else ~full_mask)
+            else:
+                ok = ok and res is None
         q.put((rank, bool(ok)))
     finally:
         dist.destroy_process_group()
