@@ -19,7 +19,7 @@
 // the TMEM allocation and the smem ring live across items; the next item's Q load and first S = Q K^T are issued under the
 // current item's O normalise + store.
 //
-// exp2: a compile-time subset (MG_ATT_POLY_MASK, default 10 of every 32) of the exponentials is evaluated on the FMA pipe (Cody-Waite range reduction by the 1.5*2^23 magic add +
+// exp2: a compile-time subset (MG_ATT_POLY_MASK, default 8 of every 32) of the exponentials is evaluated on the FMA pipe (Cody-Waite range reduction by the 1.5*2^23 magic add +
 // a degree-3 minimax polynomial on [-0.5, 0.5], max rel. error 7.5e-5 -- below the 16-bit rounding of P -- exponent inserted by
 // an integer shift-add), the rest on MUFU.EX2: the 16 MUFU lanes of an SM were the limiter (128 ex2 per row and tile).
 #include "common.cuh"
@@ -34,7 +34,8 @@ constexpr int ATT_BKV = 128;      // keys per tile
 constexpr int ATT_KV_STAGES = 5;
 constexpr int ATT_TILE_BYTES = 128 * 128;   // [128 rows][64 x 16-bit]
 #ifndef MG_ATT_POLY_MASK
-#define MG_ATT_POLY_MASK 0x4924u     // pairs 2, 5, 8, 11, 14 of the 16 pairs of a 32-column chunk: 10 of 32 exponentials on the FMA pipe
+#define MG_ATT_POLY_MASK 0x1248u     // pairs 3, 6, 9, 12 of the 16 pairs of a 32-column chunk: 8 of 32 exponentials on the FMA pipe
+                                     // (same-box A/B of the whole step, attention ms: 0/32 12.75, 8/32 11.33, 10/32 11.95, 16/32 12.49)
 #endif
 constexpr uint32_t ATT_POLY_MASK = MG_ATT_POLY_MASK;
 constexpr int ATT_THREADS = 128 + 256;   // warpgroup 0: TMA warp, MMA warp, 2 idle; warpgroups 1,2: softmax

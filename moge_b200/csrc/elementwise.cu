@@ -526,15 +526,17 @@ focal_shift_kernel(const float* __restrict__ points, const float* __restrict__ m
         if (threadIdx.x == 0) { focal_out[b] = fixed ? focal_in[b] : 1.0f; shift_out[b] = 0.0f; }
         return;
     }
-    // ---- MINPACK lmdif restated for one unknown (what scipy.optimize.least_squares(method='lm', x0=0, ftol=1e-3,
-    // xtol=gtol=1e-8, x_scale=1 -> diag=1 (mode 2), factor=100) executes in the reference, geometry_numpy.py:90,109),
-    // including its forward-difference Jacobian (fdjac2).  Reproducing its trust-region updates and its
-    // ftol stopping rule -- not just its fixed point -- keeps parity with the reference on ill-posed maps as well.
+    // ---- MINPACK lmder restated for one unknown: what scipy.optimize.least_squares(method='lm', x0=0, ftol=1e-3, xtol=gtol=1e-8,
+    // factor=100) executes in the reference (geometry_numpy.py:90,109) with SciPy >= 1.16, whose default x_scale is 'jac' ->
+    // diag=None -> MINPACK MODE 1: the variable is scaled by d = the running maximum of the Jacobian column norm, and the trust
+    // region bounds |d * step| (SciPy < 1.16 used x_scale=1, mode 2: set d = 1 below).  The solver stops on ftol = 1e-3, i.e. long
+    // before its fixed point, so the reference's answer IS its iterate sequence: reproducing the trust-region updates, the
+    // 2-point Jacobian and the stopping rule -- not just the optimum -- is what keeps depth / intrinsics within 1e-3 of it.
     const double ftol = 1e-3, xtol = 1e-8, gtol = 1e-8, epsmch = 2.220446049250313e-16, dwarf = 2.2250738585072014e-308;
     double s = 0.0;
     FsEval cur = fs_eval(s, true, x, y, z, u, v, valid, fixed, fgiven, red);
     double fnorm = sqrt(cur.cost);
-    double par = 0.0, delta = 0.0, xnorm = 0.0;
+    double par = 0.0, delta = 0.0, xnorm = 0.0, d = 1.0;
     int nfev = 1;
     bool stop = false;
     bool jac_stale = false;
@@ -546,7 +548,8 @@ focal_shift_kernel(const float* __restrict__ points, const float* __restrict__ m
         const double jtj = cur.jtj, jtr = cur.jtr;
         const double jnorm = sqrt(jtj);
         if (iter == 1) {
-            xnorm = fabs(s);
+            d = (jnorm != 0.0) ? jnorm : 1.0;                           // mode 1: diag = column norm of the first Jacobian
+            xnorm = d * fabs(s);
             delta = 100.0 * xnorm;
             if (delta == 0.0) delta = 100.0;
         }
@@ -554,18 +557,21 @@ focal_shift_kernel(const float* __restrict__ points, const float* __restrict__ m
         if (fnorm != 0.0 && jnorm != 0.0) gnorm = fabs(jtr / jnorm) / fnorm;
         if (gnorm <= gtol) break;                                   // info = 4
         if (!(jnorm > 0.0) || !isfinite(jnorm)) break;
+        d = fmax(d, jnorm);                                         // mode 1: diag = max(diag, column norm)
+        const double d2 = d * d;
         double ratio = 0.0;
         do {
-            // ---- lmpar (n = 1, R = jnorm, Q^T f = jtr / jnorm): step xs solves (jtj + par) xs = jtr, p = -xs
+            // ---- lmpar (n = 1, R = jnorm, Q^T f = jtr / jnorm, scale d): step xs solves (jtj + par d^2) xs = jtr, p = -xs,
+            //      trust region on |d xs|
             const double qtb = jtr / jnorm;
             double xs = qtb / jnorm;
-            double dxnorm = fabs(xs);
+            double dxnorm = d * fabs(xs);
             double fp = dxnorm - delta;
             if (fp <= 0.1 * delta) {
                 par = 0.0;
             } else {
-                double parl = (fp / delta) * jtj;
-                const double gn = fabs(jtr);
+                double parl = (fp / delta) * jtj / d2;
+                const double gn = fabs(jtr) / d;
                 double paru = gn / delta;
                 if (paru == 0.0) paru = dwarf / fmin(delta, 0.1);
                 par = fmax(par, parl);
@@ -573,26 +579,26 @@ focal_shift_kernel(const float* __restrict__ points, const float* __restrict__ m
                 if (par == 0.0) par = gn / dxnorm;
                 for (int k = 1;; ++k) {
                     if (par == 0.0) par = fmax(dwarf, 0.001 * paru);
-                    xs = jtr / (jtj + par);
-                    dxnorm = fabs(xs);
+                    xs = jtr / (jtj + par * d2);
+                    dxnorm = d * fabs(xs);
                     const double temp = fp;
                     fp = dxnorm - delta;
                     if (fabs(fp) <= 0.1 * delta || (parl == 0.0 && fp <= temp && temp < 0.0) || k == 10) break;
-                    const double parc = (fp / delta) * (jtj + par);
+                    const double parc = (fp / delta) * (jtj + par * d2) / d2;
                     if (fp > 0.0) parl = fmax(parl, par);
                     if (fp < 0.0) paru = fmin(paru, par);
                     par = fmax(parl, par + parc);
                 }
             }
             const double pstep = -xs;
-            const double pnorm = fabs(pstep);
+            const double pnorm = d * fabs(pstep);
             if (iter == 1) delta = fmin(delta, pnorm);
             FsEval nxt = fs_eval(s + pstep, false, x, y, z, u, v, valid, fixed, fgiven, red);
             ++nfev;
             const double fnorm1 = sqrt(nxt.cost);
             double actred = -1.0;
             if (0.1 * fnorm1 < fnorm) actred = 1.0 - (fnorm1 / fnorm) * (fnorm1 / fnorm);
-            const double temp1 = jnorm * pnorm / fnorm, temp2 = sqrt(par) * pnorm / fnorm;
+            const double temp1 = jnorm * fabs(pstep) / fnorm, temp2 = sqrt(par) * pnorm / fnorm;
             const double prered = temp1 * temp1 + 2.0 * temp2 * temp2;
             const double dirder = -(temp1 * temp1 + temp2 * temp2);
             ratio = (prered != 0.0) ? actred / prered : 0.0;
@@ -609,7 +615,7 @@ focal_shift_kernel(const float* __restrict__ points, const float* __restrict__ m
                 s += pstep;
                 cur = nxt;
                 jac_stale = true;
-                xnorm = fabs(s);
+                xnorm = d * fabs(s);
                 fnorm = fnorm1;
             }
             if (fabs(actred) <= ftol && prered <= ftol && 0.5 * ratio <= 1.0) stop = true;      // info = 1 (scipy status 2)

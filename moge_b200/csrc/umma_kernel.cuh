@@ -432,10 +432,14 @@ __device__ __forceinline__ void epilogue_tile(const UmmaParams& p, int mt, int n
         float ln_rs[8], st1[8], st2[8];        // st1/st2 (producers): partial sums of x and x^2 of this lane's 8 rows
 #pragma unroll
         for (int i = 0; i < 8; ++i) { ln_rs[i] = ln_on ? lnr.rs[i] : 1.f; st1[i] = 0.f; st2[i] = 0.f; }
+        // (Prefetching the fp32 residual of chunk c + 1 before chunk c is drained -- two chunks of loads in flight per warp -- was
+        // measured on one box, A/B: proj 3.68 -> 4.14 ms, fc2 7.24 -> 7.33 ms per step, i.e. SLOWER; the extra 32 registers and the
+        // deeper load queue cost more than the latency they hide.  Kept load-then-use.)
 #pragma unroll 1
         for (int c = 0; c < COLS; c += 32) {
             float v[32];
             tmem_ld32(t_addr + c, v);
+            float4 pre[8];
             tc_wait_ld();
 #pragma unroll
             for (int q = 0; q < 8; ++q)
@@ -462,7 +466,6 @@ __device__ __forceinline__ void epilogue_tile(const UmmaParams& p, int mt, int n
             }
             // ---- phase 1: issue every global READ of this chunk (residual / pos table / skip) back to back, so
             //      their L2 latencies overlap instead of serialising behind the stores of the previous row
-            float4 pre[8];
             int sY[8], sX[8];
 #pragma unroll
             for (int i = 0; i < 8; ++i) {

@@ -377,6 +377,18 @@ def test_benchmark_shapes_match_reference_golden(name, golden_dir):
     assert set(out.keys()) == set(gold["forward"].keys())
     tols, base = tolerances(meta, "fp16")
     check_forward(out, gold["forward"], base, s, tols)
+    if opt.get("well_posed"):
+        # cut point: the focal/shift kernel against SciPy's MINPACK on the engine's own forward outputs.  The solve stops on
+        # ftol = 1e-3, far from its fixed point, so parity means following SciPy's iterate sequence (elementwise.cu, K18)
+        from moge_b200 import capi
+        from gpu_util import stream
+        f_g = torch.empty(B, device=DEV); s_g = torch.empty(B, device=DEV)
+        capi.check(capi.lib().moge_recover_focal_shift(out["points"].data_ptr(), out["mask"].data_ptr(), None, B, H, W, None,
+                                                       f_g.data_ptr(), s_g.data_ptr(), stream()))
+        torch.cuda.synchronize()
+        f_p, s_p = moge_port.recover_focal_shift(out["points"].cpu(), out["mask"].cpu() > 0.5)
+        print("focal/shift engine", f_g.tolist(), s_g.tolist(), "scipy", f_p.tolist(), s_p.tolist())
+        assert torch.allclose(f_g.cpu(), f_p, rtol=2e-4, atol=1e-6) and torch.allclose(s_g.cpu(), s_p, rtol=2e-4, atol=2e-5)
     inf = model.infer(img, num_tokens=meta["num_tokens"])
     torch.cuda.synchronize()
     ginf = gold["infer"]

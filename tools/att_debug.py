@@ -17,9 +17,14 @@ f(); f(); counters(1)
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 e0.record(); f(); e1.record(); torch.cuda.synchronize()
 c = counters(1)
-n = B * heads * ((N + 255) // 256)
+nq = (N + 255) // 256
+items = B * heads * nq
 nkv = (N + 127) // 128
-life = c[5] / n
-print(f"attention B={B} N={N}: {e0.elapsed_time(e1):.3f} ms, {n} CTAs, lifetime {life:.0f} cyc/CTA, {nkv} kv tiles -> loop {c[2]/n/nkv:.0f} cyc per kv tile")
-for name, v in zip(["softmax(w4) waits S", "softmax(w4) waits PV(j-1)", "softmax(w4) loop total", "MMA waits P", "MMA waits K/V", "lifetime", "prologue (start -> first S)", "epilogue (O norm + store)"], c):
-    print(f"   {name:32s} {v/n:10.0f} cyc  = {v/n/life*100:5.1f} % of lifetime")
+ctas = min(items, torch.cuda.get_device_properties(0).multi_processor_count)
+life = c[5] / ctas
+tiles = items * nkv / ctas          # kv-tile iterations of one softmax group per CTA (group 0 takes part in every item)
+print(f"attention B={B} N={N}: {e0.elapsed_time(e1):.3f} ms, {items} items on {ctas} persistent CTAs, lifetime {life:.0f} cyc/CTA, "
+      f"{tiles:.0f} kv tiles per CTA -> {life / tiles:.0f} cyc per kv tile (pair of query tiles)")
+for name, v in zip(["softmax(w4) waits S", "softmax(w4) waits PV(j-1)", "softmax(w4) kv loops total", "MMA waits P / S-free", "MMA waits Q/K/V",
+                    "lifetime", "-", "softmax(w4) epilogues (wait last PV + O norm + store)"], c):
+    print(f"   {name:56s} {v/ctas:12.0f} cyc  = {v/ctas/life*100:5.1f} % of lifetime   {v/ctas/tiles:8.0f} cyc / kv tile")
