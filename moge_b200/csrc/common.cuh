@@ -55,8 +55,10 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
     return ok != 0;
 }
 // Bounded wait: a broken pipeline traps (-> cudaErrorLaunchFailure on the host) instead of hanging the GPU.
+// (every failed try_wait suspends the thread for a system-dependent time, measured ~5 us on B200: 2^21 spins ~ 10 s, far beyond
+// any legitimate wait inside a millisecond kernel; 2^26 turned a deadlock into a 5-minute hang)
 #ifndef MG_WATCHDOG_SPINS
-#define MG_WATCHDOG_SPINS (1u << 26)
+#define MG_WATCHDOG_SPINS (1u << 21)
 #endif
 constexpr int kMaxDynSmem = 232448;       // 227 KB: the opt-in dynamic shared memory limit of one CTA on sm_100
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {

@@ -65,7 +65,11 @@ def main():
                 env["MOGE_B200_LIB"] = os.path.join(ROOT, "moge_b200", "_lib", f"libmoge_b200_{v}.so")
             else:
                 env.pop("MOGE_B200_LIB", None)
-            out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True)
+            try:
+                out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=240)
+            except subprocess.TimeoutExpired:
+                print(v, "TIMEOUT")
+                continue
             if out.returncode != 0:
                 print(v, "FAILED", out.stderr[-800:])
                 continue
