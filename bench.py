@@ -24,6 +24,10 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+# One hardware work queue per CUDA stream (default: 8 queues shared by all streams of the process).  The gather / copy side streams
+# must never share a queue with the compute stream: a stream that waits for a peer's flag would stall the kernels queued behind it.
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
 import torch  # noqa: E402
 
 
@@ -42,7 +46,7 @@ def parse():
     ap.add_argument("--tokens", type=int, default=1369, help="requested base tokens (1369 -> native 37x37 grid at 518 px)")
     ap.add_argument("--dtype", default="fp16", choices=["fp16", "bf16"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--cpu-images", type=int, default=2)
+    ap.add_argument("--cpu-images", type=int, default=12, help="bounded CPU sample: single-image infers of the oracle port (~1.3 s each on 16 cores)")
     ap.add_argument("--dump-ops", default=None, help="write the per-launch profile (name, ms, flops, bytes) to this JSON file")
     ap.add_argument("--config", type=int, default=0, help="0: the driver's default line (BASELINE.json configs[1]/[3]); 3: mixed-aspect "
                     "~700-token ViT-L-normal bf16 batch (configs[2]); 5: ViT-B resolution / aspect sweep (configs[4])")
@@ -327,23 +331,37 @@ def run_engine(a):
     gather = None
     ms_gather = None
     if world > 1:
-        gat = parallel.OutputGatherer([B] * world, device=dev)
+        def run_gather(gat):
+            def step_gather():
+                gat.submit(model.infer(dev_in, num_tokens=a.tokens))
 
-        def step_gather():
-            gat.submit(model.infer(dev_in, num_tokens=a.tokens))
+            def step_gather_serial():
+                gat.submit(model.infer(dev_in, num_tokens=a.tokens))
+                gat.fence()
 
-        def step_gather_serial():
-            gat.submit(model.infer(dev_in, num_tokens=a.tokens))
-            gat.fence()
+            for _ in range(2):
+                step_gather()                                   # first calls set up the channels / buffers
+            gat.wait()
+            barrier()
+            return timed(step_gather, a.steps, fence=gat.fence), timed(step_gather_serial, a.steps, fence=gat.fence)
 
-        for _ in range(2):
-            step_gather()                                       # first calls set up the P2P channels / buffers
-        gat.wait()
-        ms_gather = timed(step_gather, a.steps, fence=gat.fence)
-        ms_gather_serial = timed(step_gather_serial, a.steps, fence=gat.fence)
+        # (a) product path: peer-memory gather -- IPC-mapped staging slots pulled by rank 0's copy engines, device-side flags,
+        #     no SM time (moge_b200.parallel.PeerGatherer over libmoge_b200's moge_peer_* entry points)
+        gat = parallel.PeerGatherer([B] * world, dev)
+        ms_gather, ms_gather_serial = run_gather(gat)
+        # (b) for comparison: the same gather as grouped NCCL isend/irecv on a side stream (copy kernels on both ends)
+        gat_nccl = parallel.OutputGatherer([B] * world, device=dev)
+        ms_nccl, ms_nccl_serial = run_gather(gat_nccl)
         gather = {"bytes_to_rank0_per_step": d2h_bytes * (world - 1), "ms_per_step_pipelined": ms_gather / a.steps,
                   "ms_per_step_serial": ms_gather_serial / a.steps, "ms_per_step_no_gather": ms_dev / a.steps,
-                  "api": "moge_b200.parallel.OutputGatherer.submit(infer(...)) per step, fence() at the end"}
+                  "api": "moge_b200.parallel.PeerGatherer.submit(infer(...)) per step, fence() at the end: CUDA-IPC staging slots, "
+                         "copy-engine pulls by rank 0, device-side flags; no SM time",
+                  "nccl_isend_irecv": {"ms_per_step_pipelined": ms_nccl / a.steps, "ms_per_step_serial": ms_nccl_serial / a.steps,
+                                       "api": "moge_b200.parallel.OutputGatherer (grouped NCCL isend/irecv on a side stream)"}}
+        if gat.debug:
+            gather["debug_ms"] = gat.debug_report()
+            print(f"[rank {rank}] gather debug (ms): {gather['debug_ms']}", file=sys.stderr, flush=True)
+        gat.close()
 
     if rank != 0:
         if world > 1:
@@ -402,12 +420,13 @@ def run_engine(a):
                           "share_of_step": t * 1e3 / total_prof_ms}
     other_ms = total_prof_ms - roofline["ms_per_step"] - roofline_decoder["ms_per_step"] - roofline_attention["ms_per_step"]
 
-    # ---- batch-1 latency (BASELINE.json configs[1]): p50 over 30 device-timed single-image infers
+    # ---- batch-1 latency (BASELINE.json configs[1]): p50 / p90 over 200 device-timed single-image infers after 20 warm-ups; every
+    #      call gets a fresh input tensor address and fresh output tensors (the graph covers the workspace-only launches)
     one = dev_in[:1].contiguous()
-    for _ in range(5):
+    for _ in range(20):
         model.infer(one, num_tokens=a.tokens)
     lat = []
-    for _ in range(30):
+    for _ in range(200):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         model.infer(one, num_tokens=a.tokens)

@@ -124,6 +124,20 @@ int moge_postprocess(float* points, const float* normal_in, const float* mask_pr
                      const float* focal, const float* shift, int B, int H, int W, int force_projection, int apply_mask,
                      float* depth, float* normal_out, uint8_t* mask_out, float* intrinsics, void* stream);
 
+/* ---- output gather over NVLink peer memory ("gather of outputs to rank 0"; BASELINE.json configs[3]).  No reference
+ * counterpart (the reference is single-GPU).  Every rank exposes a staging buffer by CUDA IPC (moge_peer_alloc -> 64-byte handle,
+ * exchanged by the caller, e.g. torch.distributed.all_gather_object), the gathering rank maps them (moge_peer_open) and pulls with
+ * copy-engine DMAs (moge_peer_copy); steps are ordered by flags in peer memory: moge_peer_flag_set makes `*flag = value` visible
+ * system-wide after everything earlier on `stream`; moge_peer_flag_wait blocks `stream` until `*flag >= value` (the flag may live on
+ * another GPU).  No SM is used for the transfer.  Python: moge_b200.parallel.PeerGatherer. */
+int moge_peer_alloc(size_t bytes, void** dev_ptr, unsigned char* handle64);
+int moge_peer_free(void* dev_ptr);
+int moge_peer_open(const unsigned char* handle64, void** dev_ptr);
+int moge_peer_close(void* dev_ptr);
+int moge_peer_copy(void* dst, const void* src, size_t bytes, void* stream);
+int moge_peer_flag_set(int* flag, int value, void* stream);
+int moge_peer_flag_wait(const int* flag, int value, void* stream);
+
 /* ---- operator-level entry points (same kernels the engine launches; used by the parity tests and micro-benchmarks)
  * y = epilogue(x[M,K] @ w[N,K]^T): epi 0 = +bias -> 16-bit, 1 = +bias,GELU(erf) -> 16-bit,
  * 2 = out32[M,N] += gamma * (acc + bias).  x, w: 16-bit (dtype MOGE_F16/MOGE_BF16), K % 8 == 0, N % 128 == 0.       */

@@ -22,7 +22,8 @@ EXPORTS = [
     "moge_last_error", "moge_version", "moge_engine_create", "moge_engine_destroy", "moge_engine_set_weight",
     "moge_engine_finalize", "moge_engine_workspace_bytes", "moge_engine_forward", "moge_engine_workspace_bytes_groups",
     "moge_engine_forward_groups", "moge_engine_num_ops", "moge_engine_op_info", "moge_engine_profile", "moge_recover_focal_shift",
-    "moge_postprocess", "moge_op_linear", "moge_op_linear_ln", "moge_op_attention", "moge_op_layernorm", "moge_op_conv",
+    "moge_postprocess", "moge_peer_alloc", "moge_peer_free", "moge_peer_open", "moge_peer_close", "moge_peer_copy", "moge_peer_flag_set",
+    "moge_peer_flag_wait", "moge_op_linear", "moge_op_linear_ln", "moge_op_attention", "moge_op_layernorm", "moge_op_conv",
 ]
 
 
@@ -87,6 +88,13 @@ def lib() -> C.CDLL:
     L.moge_engine_profile.argtypes = [vp, C.POINTER(C.c_float), ci, vp]
     L.moge_recover_focal_shift.argtypes = [vp, vp, vp, ci, ci, ci, vp, vp, vp, vp]
     L.moge_postprocess.argtypes = [vp, vp, vp, vp, vp, vp, ci, ci, ci, ci, ci, vp, vp, vp, vp, vp]
+    L.moge_peer_alloc.argtypes = [C.c_size_t, C.POINTER(vp), C.c_char_p]
+    L.moge_peer_free.argtypes = [vp]
+    L.moge_peer_open.argtypes = [C.c_char_p, C.POINTER(vp)]
+    L.moge_peer_close.argtypes = [vp]
+    L.moge_peer_copy.argtypes = [vp, vp, C.c_size_t, vp]
+    L.moge_peer_flag_set.argtypes = [vp, ci, vp]
+    L.moge_peer_flag_wait.argtypes = [vp, ci, vp]
     L.moge_op_linear.argtypes = [vp, vp, vp, vp, vp, ci, ci, ci, ci, ci, vp]
     L.moge_op_linear_ln.argtypes = [vp, vp, vp, vp, vp, vp, ci, ci, ci, ci, ci, vp]
     L.moge_op_attention.argtypes = [vp, vp, ci, ci, ci, ci, ci, vp]

@@ -161,3 +161,186 @@ class OutputGatherer:
         if self.cuda:
             self.fence()
             torch.cuda.current_stream(self.device).synchronize()
+
+
+class PeerGatherer:
+    """The output gather of BASELINE.json configs[3] over NVLink peer memory, with ZERO SM time (libmoge_b200's moge_peer_* entry
+    points): every rank copies its step outputs into an IPC-exported staging slot and raises a flag; rank `dst` waits for the flag
+    (a one-thread poll kernel on a side stream), PULLS the slot with copy-engine DMAs straight into its preallocated full-batch
+    buffers and raises a "consumed" flag the producers check before they reuse the slot.  Nothing blocks the host; the transfer of
+    step i runs under the compute of step i+1 and, unlike a NCCL send/recv pair, without copy kernels competing for SMs with the
+    engine's persistent one-CTA-per-SM kernels.  `torch.distributed` (any backend) is used once, to exchange the IPC handles.
+
+        gat = PeerGatherer([B] * world, device)        # collective: every rank constructs it
+        res = gat.submit(model.infer(x))               # every step; on `dst`: dict of full-batch buffers (valid after fence/wait)
+        gat.fence()                                    # current stream waits for everything submitted so far
+    """
+
+    SLOTS = 2
+
+    def __init__(self, counts: List[int], device: torch.device, dst: int = 0, group=None):
+        import ctypes as C
+        from . import capi
+        self.C, self.capi, self.L = C, capi, capi.lib()
+        self.counts, self.dst, self.group, self.device = list(counts), dst, group, device
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        self.offsets = [sum(self.counts[:r]) for r in range(self.world)]
+        self.n = 0
+        self.layout = None               # [(key, dtype, per-image shape, byte offset in a slot)] fixed by the first submit
+        self.slot_bytes = 0
+        self.stage = None                # this rank's staging buffer (device pointer), SLOTS slots + flags at the end
+        self.peers = {}                  # dst only: rank -> mapped staging pointer
+        self.flags_dst = None            # producers: mapped pointer to dst's "consumed" flags
+        self.full: List[Optional[Dict[str, torch.Tensor]]] = [None] * self.SLOTS
+        import os
+        self.debug = os.environ.get("MOGE_B200_GATHER_DEBUG") == "1"       # CUDA-event timing of the staging copy / the pulls
+        self.dbg_events = []
+        with torch.cuda.device(device):
+            self.side = [torch.cuda.Stream() for _ in range(max(1, self.world))]
+            self.done = [torch.cuda.Event() for _ in range(self.SLOTS)]
+
+    def debug_report(self):
+        """(debug mode) mean milliseconds of the timed sections, by label"""
+        torch.cuda.synchronize(self.device)
+        acc = {}
+        for label, e0, e1 in self.dbg_events:
+            acc.setdefault(label, []).append(e0.elapsed_time(e1))
+        return {k: sum(v) / len(v) for k, v in acc.items()}
+
+    def _mark(self, label, stream):
+        if not self.debug:
+            return None
+        e0 = torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        return (label, e0)
+
+    def _end(self, tok, stream):
+        if tok is not None:
+            e1 = torch.cuda.Event(enable_timing=True)
+            e1.record(stream)
+            self.dbg_events.append((tok[0], tok[1], e1))
+
+    # -- one-time setup, at the first submit (the output shapes are known then)
+    def _setup(self, local: Dict[str, torch.Tensor]):
+        C, L, capi = self.C, self.L, self.capi
+        keys = sorted(local.keys())
+        off, layout = 0, []
+        per_rank_max = max(self.counts)
+        for k in keys:
+            t = local[k]
+            per_img = t.numel() // max(t.shape[0], 1) * t.element_size()
+            layout.append((k, t.dtype, tuple(t.shape[1:]), off, per_img))
+            off += (per_img * per_rank_max + 255) // 256 * 256
+        self.layout, self.slot_bytes = layout, off
+        flag_bytes = 256
+        total = self.SLOTS * self.slot_bytes + flag_bytes
+        with torch.cuda.device(self.device):
+            ptr = C.c_void_p()
+            handle = C.create_string_buffer(64)
+            capi.check(L.moge_peer_alloc(total, C.byref(ptr), handle))
+            self.stage = ptr.value
+            self.flag_base = self.stage + self.SLOTS * self.slot_bytes        # int32 flags: [ready[s] for s] then [consumed[s] for s]
+            gathered = [None] * self.world
+            dist.all_gather_object(gathered, (self.rank, bytes(handle.raw), total), group=self.group)
+            if self.rank == self.dst:
+                for r, h, tot in gathered:
+                    if r == self.dst or not self.counts[r]:
+                        continue
+                    p = C.c_void_p()
+                    capi.check(L.moge_peer_open(h, C.byref(p)))
+                    self.peers[r] = p.value
+            else:
+                h = [g for g in gathered if g[0] == self.dst][0][1]
+                p = C.c_void_p()
+                capi.check(L.moge_peer_open(h, C.byref(p)))
+                self.flags_dst = p.value + self.SLOTS * self.slot_bytes
+        dist.barrier(group=self.group)
+
+    def _ready_flag(self, base, slot):
+        return base + self.SLOTS * self.slot_bytes + 4 * slot
+
+    def submit(self, local: Dict[str, torch.Tensor]) -> Optional[Dict[str, torch.Tensor]]:
+        C, L, capi = self.C, self.L, self.capi
+        if self.layout is None:
+            self._setup(local)
+        slot = self.n % self.SLOTS
+        seq = self.n + 1                                   # flag value of this step
+        self.n += 1
+        with torch.cuda.device(self.device):
+            cur = torch.cuda.current_stream()
+            if self.rank != self.dst:
+                if not self.counts[self.rank]:
+                    return None
+                st = cur.cuda_stream
+                if seq > self.SLOTS:                       # the slot's previous contents must have been pulled by dst
+                    capi.check(L.moge_peer_flag_wait(self.flags_dst + 4 * (self.SLOTS + slot), seq - self.SLOTS, st))
+                base = self.stage + slot * self.slot_bytes
+                tok = self._mark("producer: staging copy", cur)
+                for k, dt, shp, off, per_img in self.layout:
+                    t = local[k].contiguous()
+                    capi.check(L.moge_peer_copy(base + off, t.data_ptr(), per_img * t.shape[0], st))
+                self._end(tok, cur)
+                capi.check(L.moge_peer_flag_set(self._ready_flag(self.stage, slot), seq, st))
+                return None
+            # ---- dst: pull every peer's slot with DMAs on side streams, own outputs by a local copy
+            if self.full[slot] is None:
+                total = sum(self.counts)
+                self.full[slot] = {k: torch.empty((total,) + shp, dtype=torch.uint8 if dt == torch.bool else dt, device=self.device)
+                                   for k, dt, shp, off, per_img in self.layout}
+            full = self.full[slot]
+            ready = torch.cuda.Event()
+            ready.record(cur)
+            streams = self.side
+            for s in streams:
+                s.wait_event(ready)
+                s.wait_event(self.done[slot])              # previous consumer of this slot's full-batch buffers (none the first time)
+            o, n = self.offsets[self.rank], self.counts[self.rank]
+            with torch.cuda.stream(streams[0]):
+                for k, dt, shp, off, per_img in self.layout:
+                    t = local[k]
+                    full[k][o:o + n].copy_(t.view(torch.uint8) if t.dtype == torch.bool else t, non_blocking=True)
+            for t in local.values():
+                t.record_stream(streams[0])
+            for i, (r, base) in enumerate(sorted(self.peers.items())):
+                s = streams[1 + i % (len(streams) - 1)] if len(streams) > 1 else streams[0]
+                st = s.cuda_stream
+                tokw = self._mark("dst: wait for a peer's flag", s)
+                capi.check(L.moge_peer_flag_wait(self._ready_flag(base, slot), seq, st))
+                self._end(tokw, s)
+                tok = self._mark("dst: pull one peer", s)
+                for k, dt, shp, off, per_img in self.layout:
+                    dstp = full[k].data_ptr() + self.offsets[r] * per_img
+                    capi.check(L.moge_peer_copy(dstp, base + slot * self.slot_bytes + off, per_img * self.counts[r], st))
+                self._end(tok, s)
+            # all pulls of this slot done -> producers may reuse it
+            fin = streams[0]
+            for s in streams[1:]:
+                ev = torch.cuda.Event()
+                ev.record(s)
+                fin.wait_event(ev)
+            capi.check(L.moge_peer_flag_set(self.flag_base + 4 * (self.SLOTS + slot), seq, fin.cuda_stream))
+            self.done[slot].record(fin)
+            return {k: (v.view(torch.bool) if dt == torch.bool else v) for (k, dt, shp, off, per_img), v in
+                    ((e, full[e[0]]) for e in self.layout)}
+
+    def fence(self, stream=None) -> None:
+        with torch.cuda.device(self.device):
+            st = stream if stream is not None else torch.cuda.current_stream()
+            for ev in self.done:
+                st.wait_event(ev)
+
+    def wait(self) -> None:
+        self.fence()
+        torch.cuda.current_stream(self.device).synchronize()
+
+    def close(self) -> None:
+        L = self.L
+        with torch.cuda.device(self.device):
+            torch.cuda.synchronize()
+            for p in self.peers.values():
+                L.moge_peer_close(p)
+            if self.flags_dst is not None:
+                L.moge_peer_close(self.flags_dst - self.SLOTS * self.slot_bytes)
+            if self.stage:
+                L.moge_peer_free(self.stage)
+        self.peers, self.flags_dst, self.stage = {}, None, None

@@ -4,7 +4,7 @@
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,driver_version,memory.total --format=csv > gpurun_out/gpu_info.txt 2>&1
 rc=0
-for f in tests/test_gpu_geometry.py tests/test_gpu_ops.py tests/test_gpu_model.py; do
+for f in tests/test_gpu_geometry.py tests/test_gpu_ops.py tests/test_gpu_model.py tests/test_gpu_peer.py; do
   name=$(basename $f .py)
   timeout 900 python -m pytest $f -q -m gpu -s "$@" > gpurun_out/$name.log 2>&1
   r=$?
