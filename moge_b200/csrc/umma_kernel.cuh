@@ -12,6 +12,7 @@
 // replicate-padded conv with ReLU/residual, K17 head output projection.
 #pragma once
 #include "common.cuh"
+#include <type_traits>
 
 namespace mg {
 
@@ -88,21 +89,24 @@ template <int BN> struct UmmaCfg {
 // 7e-7 in fp32, far below the 16-bit output rounding).  5 FMA + 1 MUFU.EX2 + 4 other instructions instead of libdevice
 // erff's ~25: the fc1 epilogue is ALU-issue-bound, this is what keeps the tensor pipe fed.  (An A&S 7.1.26 variant with
 // MUFU.RCP + MUFU.EX2 was measured 25 % slower than erff: two quarter-rate MUFU ops per element are too many.)
+// (No clamp of |x|: the polynomial keeps decreasing beyond the fitted range -- q(6) = -29.2, q(8) = -51.8, q(20) = -1019 -- so
+// |x| * 2^q just underflows to 0 for large |x|; the clamp cost one instruction per element in an epilogue that is bound by
+// instruction issue.)
 __device__ __forceinline__ float gelu_erf(float x) {
-    const float ax = fminf(fabsf(x), 6.0f);
+    const float ax = fabsf(x);
     float q = fmaf(-4.804994387e-04f, ax, 7.133518346e-03f);
     q = fmaf(q, ax, -5.194617063e-02f);
     q = fmaf(q, ax, -4.598676562e-01f);
     q = fmaf(q, ax, -1.150842190e+00f);
     q = fmaf(q, ax, -3.041332639e-05f);
-    const float t = fabsf(x) * ex2_approx(q);
+    const float t = ax * ex2_approx(q);
     return fmaf(-0.5f, t, fmaxf(x, 0.0f));
 }
 
 // Two lanes of gelu_erf with packed FFMA2/FMUL2 (bit-identical to the scalar version: fma.rn.f32x2 is fmaf per lane).
 __device__ __forceinline__ float2 gelu_erf2(float2 x) {
     const float2 ab = make_float2(fabsf(x.x), fabsf(x.y));
-    const float2 ax = make_float2(fminf(ab.x, 6.0f), fminf(ab.y, 6.0f));
+    const float2 ax = ab;
     float2 q = ffma2(make_float2(-4.804994387e-04f, -4.804994387e-04f), ax, make_float2(7.133518346e-03f, 7.133518346e-03f));
     q = ffma2(q, ax, make_float2(-5.194617063e-02f, -5.194617063e-02f));
     q = ffma2(q, ax, make_float2(-4.598676562e-01f, -4.598676562e-01f));
@@ -200,8 +204,17 @@ __device__ __forceinline__ void epilogue_dec16(const UmmaParams& p, int mt, int 
         eflags[i] = (ry[i] == 0 ? 1 : 0) | (ry[i] == p.H - 1 ? 2 : 0) | (rx[i] == 0 ? 4 : 0) | (rx[i] == p.W - 1 ? 8 : 0);
     }
     const float inv_wo = 1.0f / static_cast<float>(p.Wo), inv_ho = 1.0f / static_cast<float>(p.Ho);
-#pragma unroll 1
-    for (int c = 0; c < COLS; c += 32) {
+    // Interior tiles (every pixel inside the image and none on its border: ~70 % of the tiles of a 148x148 map) take a
+    // straight-line path: no per-row validity predicates, no border-replication bookkeeping.  ncu of the ConvTranspose launch
+    // showed this epilogue spending 57 % of its instructions on address arithmetic, predicates and branches (IMAD / ISETP / BRA /
+    // LOP3 / SEL) around 21 % of useful work (FADD, F2FP, LDS / STS, STG).  The phase of a pixel-shuffle chunk comes from a shift
+    // when C_out is a power of two (every MoGe config) instead of an integer division per chunk.
+    bool interior;
+    if (AMODE == AMODE_TILES) interior = tile_y0 > 0 && tile_x0 > 0 && tile_y0 + TILE_PH < p.H && tile_x0 + TILE_PW < p.W;
+    else interior = false;
+    const int ldo_shift = ((p.ldo & (p.ldo - 1)) == 0) ? (31 - __clz(p.ldo)) : -1;
+    auto chunk = [&](int c, auto fast_tag) {
+        constexpr bool FAST = decltype(fast_tag)::value;
         float v[32];
         tmem_ld32(t_addr + c, v);
         tc_wait_ld();
@@ -212,7 +225,7 @@ __device__ __forceinline__ void epilogue_dec16(const UmmaParams& p, int mt, int 
         int co = col + 8 * q8, qd = 0, qmask = 15;
         size_t qoff = 0;
         if (shuffle) {
-            qd = col / p.ldo;                              // ldo == C_out; a 32-column chunk never straddles a phase
+            qd = (ldo_shift >= 0) ? (col >> ldo_shift) : (col / p.ldo);      // ldo == C_out; a 32-column chunk never straddles a phase
             co -= qd * p.ldo;
             qoff = (static_cast<size_t>(qd >> 1) * p.Wop + (qd & 1)) * p.ldo * 2;
             qmask = ((qd >> 1) ? 2 : 1) | ((qd & 1) ? 8 : 4);
@@ -229,7 +242,7 @@ __device__ __forceinline__ void epilogue_dec16(const UmmaParams& p, int mt, int 
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             sk[i] = make_uint4(0u, 0u, 0u, 0u);
-            if (has_skip && ok[i]) sk[i] = *reinterpret_cast<const uint4*>(static_cast<const uint8_t*>(p.skip) + roff[i] + qoff);
+            if (has_skip && (FAST || ok[i])) sk[i] = *reinterpret_cast<const uint4*>(static_cast<const uint8_t*>(p.skip) + roff[i] + qoff);
         }
         // phase 2: math + 16-byte stores
         uint4 pk_raw[4], pk_relu[4];
@@ -239,7 +252,7 @@ __device__ __forceinline__ void epilogue_dec16(const UmmaParams& p, int mt, int 
             const int rl = 8 * i + sub;
             float4 a0 = scr[rl * 8 + ((2 * q8) ^ (rl & 7))];
             float4 a1 = scr[rl * 8 + ((2 * q8 + 1) ^ (rl & 7))];
-            if (!ok[i]) continue;
+            if (!FAST && !ok[i]) continue;
             a0.x += b0.x; a0.y += b0.y; a0.z += b0.z; a0.w += b0.w;
             a1.x += b1.x; a1.y += b1.y; a1.z += b1.z; a1.w += b1.w;
             if (has_skip) {
@@ -254,7 +267,7 @@ __device__ __forceinline__ void epilogue_dec16(const UmmaParams& p, int mt, int 
                 a0.x += g0.x * uu + h0.x * vv; a0.y += g0.y * uu + h0.y * vv; a0.z += g0.z * uu + h0.z * vv; a0.w += g0.w * uu + h0.w * vv;
                 a1.x += g1.x * uu + h1.x * vv; a1.y += g1.y * uu + h1.y * vv; a1.z += g1.z * uu + h1.z * vv; a1.w += g1.w * uu + h1.w * vv;
             }
-            if ((eflags[i] & qmask) != 0) edge_rows |= 1u << i;
+            if (!FAST && (eflags[i] & qmask) != 0) edge_rows |= 1u << i;
             if (has_raw) {
                 pk_raw[i] = make_uint4(H::pack(a0.x, a0.y), H::pack(a0.z, a0.w), H::pack(a1.x, a1.y), H::pack(a1.z, a1.w));
                 *reinterpret_cast<uint4*>(static_cast<uint8_t*>(p.out0) + roff[i] + qoff) = pk_raw[i];
@@ -265,7 +278,7 @@ __device__ __forceinline__ void epilogue_dec16(const UmmaParams& p, int mt, int 
                 *reinterpret_cast<uint4*>(static_cast<uint8_t*>(p.out1) + roff[i] + qoff) = pk_relu[i];
             }
         }
-        if (edge_rows != 0) {
+        if (!FAST && edge_rows != 0) {
 #pragma unroll
             for (int i = 0; i < 4; ++i)
                 if (edge_rows >> i & 1) {
@@ -275,6 +288,13 @@ __device__ __forceinline__ void epilogue_dec16(const UmmaParams& p, int mt, int 
                 }
         }
         __syncwarp();
+    };
+    if (interior) {
+#pragma unroll 1
+        for (int c = 0; c < COLS; c += 32) chunk(c, std::true_type{});
+    } else {
+#pragma unroll 1
+        for (int c = 0; c < COLS; c += 32) chunk(c, std::false_type{});
     }
 }
 
@@ -435,8 +455,10 @@ __device__ __forceinline__ void epilogue_tile(const UmmaParams& p, int mt, int n
         // (Prefetching the fp32 residual of chunk c + 1 before chunk c is drained -- two chunks of loads in flight per warp -- was
         // measured on one box, A/B: proj 3.68 -> 4.14 ms, fc2 7.24 -> 7.33 ms per step, i.e. SLOWER; the extra 32 registers and the
         // deeper load queue cost more than the latency they hide.  Kept load-then-use.)
-#pragma unroll 1
-        for (int c = 0; c < COLS; c += 32) {
+        // Full row tiles (all but the last of a GEMM) take a path without the per-row validity predicates.
+        const bool full_tile = (AMODE == AMODE_ROWS) && (static_cast<long>(mt) + 1) * TILE_M <= static_cast<long>(p.M);
+        auto chunk = [&](int c, auto full_tag) {
+            constexpr bool FULL = decltype(full_tag)::value;
             float v[32];
             tmem_ld32(t_addr + c, v);
             float4 pre[8];
@@ -472,7 +494,7 @@ __device__ __forceinline__ void epilogue_tile(const UmmaParams& p, int mt, int n
                 pre[i] = make_float4(0.f, 0.f, 0.f, 0.f);
                 sY[i] = ry[i]; sX[i] = rx[i];
                 if (EPI == EPI_DEC && shuffle) { sY[i] = 2 * ry[i] + (qd >> 1); sX[i] = 2 * rx[i] + (qd & 1); }
-                if (!ok[i]) continue;
+                if (!FULL && !ok[i]) continue;
                 if (EPI == EPI_RESID) {
                     pre[i] = *reinterpret_cast<const float4*>(static_cast<const float*>(p.out0) + roff[i] + co);
                 } else if (EPI == EPI_PATCH) {
@@ -491,7 +513,7 @@ __device__ __forceinline__ void epilogue_tile(const UmmaParams& p, int mt, int n
             for (int i = 0; i < 8; ++i) {
                 const int rl = 4 * i + sub;
                 float4 a = scr[rl * 8 + (q4 ^ (rl & 7))];
-                if (!ok[i]) continue;
+                if (!FULL && !ok[i]) continue;
                 if (EPI == EPI_STORE16 || EPI == EPI_GELU16) {
                     // (packed FADD2 for the plain bias add measured ~5 % SLOWER on these GEMMs than four scalar FADDs -- three boxes
                     // each way -- although the packed GELU polynomial and the packed attention softmax are wins; kept scalar)
@@ -563,6 +585,13 @@ __device__ __forceinline__ void epilogue_tile(const UmmaParams& p, int mt, int n
                     }
             }
             __syncwarp();
+        };
+        if (full_tile) {
+#pragma unroll 1
+            for (int c = 0; c < COLS; c += 32) chunk(c, std::true_type{});
+        } else {
+#pragma unroll 1
+            for (int c = 0; c < COLS; c += 32) chunk(c, std::false_type{});
         }
         // LayerNorm fold, producer side: partial (sum, sum of squares) of this warp's column group for each of its rows
         if (x16_on) {
