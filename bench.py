@@ -383,9 +383,9 @@ def run_engine(a):
         return idx, t, sum(ops[i][1] for i in idx), sum(ops[i][2] for i in idx)
 
     # DRAM traffic of the dominant launch of each class, from the committed `ncu --set full` capture of this workload
-    # (profiles/r1_ncu_traffic.json; per launch, like `achieved`); null for any other workload
+    # (profiles/r2_ncu_traffic.json; per launch, like `achieved`); null for any other workload
     traffic = {}
-    tpath = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r1_ncu_traffic.json")
+    tpath = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r2_ncu_traffic.json")
     if a.size == "vitl" and B == 32 and R == 518 and a.tokens == 1369 and a.dtype == "fp16" and os.path.exists(tpath):
         with open(tpath) as fh:
             traffic = json.load(fh)

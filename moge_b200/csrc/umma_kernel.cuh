@@ -459,16 +459,26 @@ __device__ __forceinline__ void epilogue_tile(const UmmaParams& p, int mt, int n
         const bool full_tile = (AMODE == AMODE_ROWS) && (static_cast<long>(mt) + 1) * TILE_M <= static_cast<long>(p.M);
         auto chunk = [&](int c, auto full_tag) {
             constexpr bool FULL = decltype(full_tag)::value;
+            const int col = nt * BN + col_begin + c;       // first global output column of this chunk
+            int co = col + 4 * q4;                         // this lane's 4 columns
+            float4 pre[8];
+            // EPI_RESID (proj / fc2): the fp32 residual reads do not depend on the accumulator -- they are issued FIRST, so that
+            // their HBM latency runs under the TMEM load and the transpose (ncu: these launches stall on long_scoreboard, 7.6 warps
+            // per issue cycle, at 48 % of the DRAM peak: bound by loads in flight, not by bandwidth)
+            if (EPI == EPI_RESID) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    pre[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (FULL || ok[i]) pre[i] = *reinterpret_cast<const float4*>(static_cast<const float*>(p.out0) + roff[i] + co);
+                }
+            }
             float v[32];
             tmem_ld32(t_addr + c, v);
-            float4 pre[8];
             tc_wait_ld();
 #pragma unroll
             for (int q = 0; q < 8; ++q)
                 scr[lane * 8 + (q ^ (lane & 7))] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
             __syncwarp();
-            const int col = nt * BN + col_begin + c;       // first global output column of this chunk
-            int co = col + 4 * q4;                         // this lane's 4 columns
             int qd = 0;
             size_t qoff = 0;                               // EPI_DEC: byte offset of this chunk relative to the centre pixel
             int qmask = 15;                                // which source-grid edges replicate for this chunk
@@ -491,12 +501,12 @@ __device__ __forceinline__ void epilogue_tile(const UmmaParams& p, int mt, int n
             int sY[8], sX[8];
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-                pre[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (EPI != EPI_RESID) pre[i] = make_float4(0.f, 0.f, 0.f, 0.f);
                 sY[i] = ry[i]; sX[i] = rx[i];
                 if (EPI == EPI_DEC && shuffle) { sY[i] = 2 * ry[i] + (qd >> 1); sX[i] = 2 * rx[i] + (qd & 1); }
                 if (!FULL && !ok[i]) continue;
                 if (EPI == EPI_RESID) {
-                    pre[i] = *reinterpret_cast<const float4*>(static_cast<const float*>(p.out0) + roff[i] + co);
+                    // (loaded at the top of the chunk)
                 } else if (EPI == EPI_PATCH) {
                     const int t = ry[i] * p.W + rx[i];
                     pre[i] = *reinterpret_cast<const float4*>(p.vec1 + static_cast<size_t>(t) * p.ldo + co);

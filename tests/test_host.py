@@ -139,12 +139,13 @@ def test_serving_pipeline_needs_a_cuda_model():
         InferPipeline(m, depth=0)
 
 
-def test_committed_bench_lines_follow_the_contract():
-    """profiles/r1_bench_n1.json and r1_bench_reference_arm.json are real bench.py lines: check the keys the driver parses."""
+@pytest.mark.parametrize("tag", ["r1", "r2"])
+def test_committed_bench_lines_follow_the_contract(tag):
+    """profiles/<tag>_bench_n1.json and <tag>_bench_reference_arm.json are real bench.py lines: check the keys the driver parses."""
     import json
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    eng = json.load(open(os.path.join(root, "profiles", "r1_bench_n1.json")))
-    ref = json.load(open(os.path.join(root, "profiles", "r1_bench_reference_arm.json")))
+    eng = json.load(open(os.path.join(root, "profiles", f"{tag}_bench_n1.json")))
+    ref = json.load(open(os.path.join(root, "profiles", f"{tag}_bench_reference_arm.json")))
     for line in (eng, ref):
         for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
                   "dtype", "data", "config", "e2e", "cpu_baseline", "gpu_launches"):
@@ -162,3 +163,20 @@ def test_committed_bench_lines_follow_the_contract():
         assert k in r, k
     assert abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9
     assert {"sm_mhz", "sm_max_mhz", "reasons"} <= set(eng["clocks"])
+    if tag == "r2":
+        gb = eng["gpu_baseline"]                              # same-box PyTorch-CUDA comparator, both 16-bit modes of the reference
+        for mode in ("half", "autocast"):
+            assert gb[mode]["batch1_iters"] >= 200 and gb[mode]["images_per_s"] > 0
+        assert eng["latency"]["iters"] >= 200
+        assert "SURVEY" in eng["roofline_decoder"]["bytes_definition"] and eng["roofline_decoder"]["frac_engine_bytes"] < eng["roofline_decoder"]["frac"]
+        n8 = json.load(open(os.path.join(root, "profiles", "r2_bench_n8.json")))
+        assert n8["n_gpus"] == 8 and n8["value"] == n8["value_with_gather"] and n8["value"] < n8["value_compute_only"]
+        assert n8["gather"]["bytes_to_rank0_per_step"] == 7 * eng["e2e"]["d2h_bytes_per_step"]
+
+
+def test_all_committed_profile_json_files_parse():
+    import glob
+    import json
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for f in glob.glob(os.path.join(root, "profiles", "*.json")):
+        json.load(open(f))
