@@ -83,6 +83,7 @@ __device__ __forceinline__ float2 ex2_poly2(float2 x) {
 template <bool BF16>
 __global__ void __launch_bounds__(ATT_THREADS, 1)
 attention_kernel(const __grid_constant__ CUtensorMap mapQKV, const AttnParams p) {
+    pdl_launch_dependents();      // (the wait sits after the barrier / TMEM set-up below: that prologue overlaps the previous kernel's tail)
     using H = H16<BF16>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -128,6 +129,7 @@ attention_kernel(const __grid_constant__ CUtensorMap mapQKV, const AttnParams p)
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
+    pdl_wait();
     // TMEM columns: S0 [0,128)  S1 [128,256)  O0 [256,320)  O1 [320,384)  P0 [384,448)  P1 [448,512)  (P: 2 x 16-bit per column)
     // Barrier phases: every barrier is waited on by "completion index" (a running count that survives item boundaries):
     // completion k of a barrier is observed with parity k & 1.
@@ -438,8 +440,7 @@ int launch_attention(const CUtensorMap& mapQKV, void* out, const AttnItem* items
     auto kern = bf16 ? attention_kernel<true> : attention_kernel<false>;
     if (bf16) MG_SET_SMEM_ONCE(attention_kernel<true>, ATT_SMEM);
     else MG_SET_SMEM_ONCE(attention_kernel<false>, ATT_SMEM);
-    kern<<<ncta, ATT_THREADS, ATT_SMEM, st>>>(mapQKV, p);
-    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(launch_pdl(kern, dim3(ncta), dim3(ATT_THREADS), ATT_SMEM, st, mapQKV, p));
     return 0;
 }
 

@@ -26,6 +26,15 @@ __device__ __forceinline__ bool elect_one() {
     return pred != 0;
 }
 
+// Programmatic dependent launch: let the next kernel in the stream start launching, then wait until the previous grid has
+// completed and its writes are visible (no-ops when the kernel was not launched with programmatic stream serialization).
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_prologue() {
+    pdl_launch_dependents();
+    pdl_wait();
+}
+
 // -------------------------------------------------------------------------------------------- mbarrier
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");

@@ -13,8 +13,7 @@ static int launch_inst(const CUtensorMap& a, const CUtensorMap& aux, const CUten
     int grid = (num_sms / nnt) * nnt;
     if (p.num_m_tiles * nnt < grid) grid = p.num_m_tiles * nnt;
     if (grid <= 0) return 0;
-    kern<<<grid, Cfg::kThreads, Cfg::kSmemBytes, st>>>(a, aux, w, p);
-    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(launch_pdl(kern, dim3(grid), dim3(Cfg::kThreads), Cfg::kSmemBytes, st, a, aux, w, p));
     return 0;
 }
 

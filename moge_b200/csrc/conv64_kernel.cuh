@@ -48,6 +48,7 @@ template <int BN, int EPI, bool BF16, int DF>
 __global__ void __launch_bounds__(Conv64Cfg<BN>::kThreads, 1)
 conv64_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapAux,
               const __grid_constant__ CUtensorMap mapW, const UmmaParams p) {
+    pdl_launch_dependents();      // (the wait sits after the barrier / TMEM set-up below: that prologue overlaps the previous kernel's tail)
     using Cfg = Conv64Cfg<BN>;
     constexpr int S = Cfg::kStages;
     extern __shared__ uint8_t smem_raw[];
@@ -85,6 +86,7 @@ conv64_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_wait();
 
     if (warp == 0) {
         // The whole warp walks the loop (converged) and ONE ELECTED lane issues: inside `if (lane == 0)` the compiler must

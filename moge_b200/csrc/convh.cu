@@ -12,8 +12,7 @@ static int launch_inst(const CUtensorMap& a, const CUtensorMap& aux, const CUten
     const int tiles = p.num_m_tiles * p.num_n_tiles;
     if (tiles <= 0) return 0;
     const int grid = tiles < num_sms ? tiles : num_sms;
-    kern<<<grid, Cfg::kThreads, Cfg::kSmemBytes, st>>>(a, aux, w, p);
-    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(launch_pdl(kern, dim3(grid), dim3(Cfg::kThreads), Cfg::kSmemBytes, st, a, aux, w, p));
     return 0;
 }
 

@@ -34,6 +34,7 @@ template <int BN, bool BF16, int DF>
 __global__ void __launch_bounds__(ConvhCfg<BN>::kThreads, 1)
 convh_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapAux,
              const __grid_constant__ CUtensorMap mapW, const UmmaParams p) {
+    pdl_launch_dependents();      // (the wait sits after the barrier / TMEM set-up below: that prologue overlaps the previous kernel's tail)
     using Cfg = ConvhCfg<BN>;
     constexpr int SA = Cfg::kAStages, SW = Cfg::kWStages;
     extern __shared__ uint8_t smem_raw[];
@@ -67,6 +68,7 @@ convh_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_wait();
 
     if (warp == 0) {
         // ================================================================== TMA producer (converged warp, elected lane issues)

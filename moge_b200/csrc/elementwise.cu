@@ -37,6 +37,7 @@ __device__ __forceinline__ float aa_w(const AAFilter& f, float center, int j) {
 template <bool BF16>
 __global__ void preprocess_kernel(const void* __restrict__ image, int dtype, int B, int H, int W, int h, int w,
                                   typename H16<BF16>::T* __restrict__ patches, int Kp) {
+    pdl_prologue();
     const int T = h * w;
     const size_t total = static_cast<size_t>(B) * T * Kp;
     const float mean[3] = {0.485f, 0.456f, 0.406f};
@@ -82,8 +83,8 @@ int launch_preprocess(const void* image, int image_dtype, int B, int H, int W, i
     const size_t total = static_cast<size_t>(B) * h * w * Kp;
     const int threads = 256;
     const int blocks = static_cast<int>(std::min<size_t>((total + threads - 1) / threads, 148 * 16));
-    if (bf16) preprocess_kernel<true><<<blocks, threads, 0, st>>>(image, image_dtype, B, H, W, h, w, static_cast<__nv_bfloat16*>(patches), Kp);
-    else preprocess_kernel<false><<<blocks, threads, 0, st>>>(image, image_dtype, B, H, W, h, w, static_cast<__half*>(patches), Kp);
+    if (bf16) CUDA_TRY(launch_pdl(preprocess_kernel<true>, dim3(blocks), dim3(threads), 0, st, image, image_dtype, B, H, W, h, w, static_cast<__nv_bfloat16*>(patches), Kp));
+    else CUDA_TRY(launch_pdl(preprocess_kernel<false>, dim3(blocks), dim3(threads), 0, st, image, image_dtype, B, H, W, h, w, static_cast<__half*>(patches), Kp));
     CUDA_TRY(cudaGetLastError());
     return 0;
 }
@@ -150,11 +151,12 @@ int launch_pos_table(const float* pos_embed, const float* cls_token, const float
 }
 
 __global__ void init_cls_kernel(float* __restrict__ x, const float* __restrict__ cls_row, int B, int N, int D) {
+    pdl_prologue();
     const int b = blockIdx.x;
     for (int d = threadIdx.x; d < D; d += blockDim.x) x[static_cast<size_t>(b) * N * D + d] = cls_row[d];
 }
 int launch_init_cls(float* x, const float* cls_row, int B, int N, int D, cudaStream_t st) {
-    init_cls_kernel<<<B, 256, 0, st>>>(x, cls_row, B, N, D);
+    CUDA_TRY(launch_pdl(init_cls_kernel, dim3(B), dim3(256), 0, st, x, cls_row, B, N, D));
     CUDA_TRY(cudaGetLastError());
     return 0;
 }
@@ -172,6 +174,7 @@ int launch_init_cls(float* x, const float* cls_row, int B, int N, int D, cudaStr
 template <bool BF16>
 __global__ void ln_prepare_kernel(const float* __restrict__ x, long row_stride, int D, typename H16<BF16>::T* __restrict__ x16,
                                   long row_stride16, float2* __restrict__ stats, long stats_stride, int parts) {
+    pdl_prologue();
     using H = H16<BF16>;
     const long r = blockIdx.x;
     const float* xr = x + r * row_stride;
@@ -197,14 +200,15 @@ int launch_ln_prepare(const float* x, int rows, long row_stride, int D, void* x1
                       int parts, bool bf16, cudaStream_t st) {
     if (D % 2) return set_error("ln_prepare: D must be even");
     if (rows <= 0) return 0;
-    if (bf16) ln_prepare_kernel<true><<<rows, 128, 0, st>>>(x, row_stride, D, static_cast<__nv_bfloat16*>(x16), row_stride16, stats, stats_stride, parts);
-    else ln_prepare_kernel<false><<<rows, 128, 0, st>>>(x, row_stride, D, static_cast<__half*>(x16), row_stride16, stats, stats_stride, parts);
+    if (bf16) CUDA_TRY(launch_pdl(ln_prepare_kernel<true>, dim3(rows), dim3(128), 0, st, x, row_stride, D, static_cast<__nv_bfloat16*>(x16), row_stride16, stats, stats_stride, parts));
+    else CUDA_TRY(launch_pdl(ln_prepare_kernel<false>, dim3(rows), dim3(128), 0, st, x, row_stride, D, static_cast<__half*>(x16), row_stride16, stats, stats_stride, parts));
     CUDA_TRY(cudaGetLastError());
     return 0;
 }
 
 // per-row rstd from the partial sums: rstd[r] = 1 / sqrt(E[x^2] - E[x]^2 + 1e-6)
 __global__ void ln_rstd_kernel(const float2* __restrict__ stats, int ld, int parts, int rows, float inv_d, float* __restrict__ rstd) {
+    pdl_prologue();
     const int r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= rows) return;
     float a = 0.f, b = 0.f;
@@ -214,7 +218,7 @@ __global__ void ln_rstd_kernel(const float2* __restrict__ stats, int ld, int par
 }
 int launch_ln_rstd(const float2* stats, int ld, int parts, int rows, int D, float* rstd, cudaStream_t st) {
     if (rows <= 0) return 0;
-    ln_rstd_kernel<<<(rows + 255) / 256, 256, 0, st>>>(stats, ld, parts, rows, 1.0f / static_cast<float>(D), rstd);
+    CUDA_TRY(launch_pdl(ln_rstd_kernel, dim3((rows + 255) / 256), dim3(256), 0, st, stats, ld, parts, rows, 1.0f / static_cast<float>(D), rstd));
     CUDA_TRY(cudaGetLastError());
     return 0;
 }
@@ -266,6 +270,7 @@ template <bool BF16, int VEC>   // VEC = D / 128 float4 per lane
 __global__ void layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
                                  typename H16<BF16>::T* __restrict__ out, int rows, int D, int ld_out, int col_off, int mode,
                                  int N, float* __restrict__ cls_out) {
+    pdl_prologue();
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (warp >= rows) return;
@@ -319,8 +324,8 @@ int launch_layernorm(const float* x, const float* gamma, const float* beta, void
     const int blocks = (rows + wpb - 1) / wpb;
 #define LN_CASE(V)                                                                                                        \
     case V:                                                                                                               \
-        if (bf16) layernorm_kernel<true, V><<<blocks, threads, 0, st>>>(x, gamma, beta, static_cast<__nv_bfloat16*>(out), rows, D, ld_out, col_off, mode, tokens_per_image, cls_out); \
-        else layernorm_kernel<false, V><<<blocks, threads, 0, st>>>(x, gamma, beta, static_cast<__half*>(out), rows, D, ld_out, col_off, mode, tokens_per_image, cls_out);       \
+        if (bf16) { if (launch_pdl(layernorm_kernel<true, V>, dim3(blocks), dim3(threads), 0, st, x, gamma, beta, static_cast<__nv_bfloat16*>(out), rows, D, ld_out, col_off, mode, tokens_per_image, cls_out) != cudaSuccess) return set_error("layernorm launch failed"); } \
+        else { if (launch_pdl(layernorm_kernel<false, V>, dim3(blocks), dim3(threads), 0, st, x, gamma, beta, static_cast<__half*>(out), rows, D, ld_out, col_off, mode, tokens_per_image, cls_out) != cudaSuccess) return set_error("layernorm launch failed"); }       \
         break;
     switch (D / 128) {
         LN_CASE(1) LN_CASE(2) LN_CASE(3) LN_CASE(4) LN_CASE(5) LN_CASE(6) LN_CASE(7) LN_CASE(8)
@@ -334,6 +339,7 @@ int launch_layernorm(const float* x, const float* gamma, const float* beta, void
 // moge/model/modules.py:184-192 + v2.py:167,182: exp(W3 relu(W2 relu(W1 cls + b1) + b2) + b3).  Warp per output row.
 __global__ void mlp_layer_kernel(const float* __restrict__ in, const float* __restrict__ W, const float* __restrict__ bias,
                                  float* __restrict__ out, int din, int dout, int relu, int do_exp) {
+    pdl_prologue();
     const int b = blockIdx.y;
     const int j = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
@@ -359,7 +365,7 @@ int launch_scale_head(const float* cls, const float* const* w, const float* cons
         const bool last = (l == nlayers - 1);
         float* dst = last ? out : scratch + static_cast<size_t>(l & 1) * B * maxd;
         dim3 grid((dims[l + 1] + 7) / 8, B);
-        mlp_layer_kernel<<<grid, 256, 0, st>>>(cur, w[l], bias[l], dst, dims[l], dims[l + 1], last ? 0 : 1, last ? 1 : 0);
+        CUDA_TRY(launch_pdl(mlp_layer_kernel, grid, dim3(256), 0, st, cur, w[l], bias[l], dst, dims[l], dims[l + 1], last ? 0 : 1, last ? 1 : 0));
         cur = dst;
     }
     CUDA_TRY(cudaGetLastError());
@@ -372,6 +378,7 @@ int launch_scale_head(const float* cls, const float* const* w, const float* cons
 __global__ void head_output_kernel(const float4* __restrict__ pts, const float4* __restrict__ nrm, const float* __restrict__ msk,
                                    int B, int Hl, int Wl, int H, int W, int remap, float* __restrict__ points,
                                    float* __restrict__ normal, float* __restrict__ mask) {
+    pdl_prologue();
     const size_t total = static_cast<size_t>(B) * H * W;
     const float rh = static_cast<float>(Hl) / H, rw = static_cast<float>(Wl) / W;
     for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < total;
@@ -416,7 +423,7 @@ int launch_head_output(const float4* pts_lr, const float4* nrm_lr, const float* 
     const size_t total = static_cast<size_t>(B) * H * W;
     const int threads = 256;
     const int blocks = static_cast<int>(std::min<size_t>((total + threads - 1) / threads, 148 * 16));
-    head_output_kernel<<<blocks, threads, 0, st>>>(pts_lr, nrm_lr, msk_lr, B, Hl, Wl, H, W, remap_mode, points, normal, mask);
+    CUDA_TRY(launch_pdl(head_output_kernel, dim3(blocks), dim3(threads), 0, st, pts_lr, nrm_lr, msk_lr, B, Hl, Wl, H, W, remap_mode, points, normal, mask));
     CUDA_TRY(cudaGetLastError());
     return 0;
 }
@@ -493,6 +500,7 @@ __device__ FsEval fs_eval(double s, bool with_jac, const float* x, const float* 
 __global__ void __launch_bounds__(FS_THREADS)
 focal_shift_kernel(const float* __restrict__ points, const float* __restrict__ mask_prob, const uint8_t* __restrict__ mask_u8,
                    int H, int W, const float* __restrict__ focal_in, float* __restrict__ focal_out, float* __restrict__ shift_out) {
+    pdl_prologue();
     __shared__ double red[FS_THREADS / 32];
     __shared__ int count_sh;
     const int b = blockIdx.x;
@@ -638,7 +646,7 @@ focal_shift_kernel(const float* __restrict__ points, const float* __restrict__ m
 }
 int launch_focal_shift(const float* points, const float* mask_prob, const uint8_t* mask_u8, int B, int H, int W,
                        const float* focal_in, float* focal_out, float* shift_out, cudaStream_t st) {
-    focal_shift_kernel<<<B, FS_THREADS, 0, st>>>(points, mask_prob, mask_u8, H, W, focal_in, focal_out, shift_out);
+    CUDA_TRY(launch_pdl(focal_shift_kernel, dim3(B), dim3(FS_THREADS), 0, st, points, mask_prob, mask_u8, H, W, focal_in, focal_out, shift_out));
     CUDA_TRY(cudaGetLastError());
     return 0;
 }
@@ -651,6 +659,7 @@ __global__ void postprocess_kernel(float* __restrict__ points, const float* __re
                                    const float* __restrict__ shift, int H, int W, int force_projection, int apply_mask,
                                    float* __restrict__ depth, float* __restrict__ normal_out, uint8_t* __restrict__ mask_out,
                                    float* __restrict__ intrinsics) {
+    pdl_prologue();
     const int b = blockIdx.y;
     const float aspect = static_cast<float>(W) / H;
     const float diag = sqrtf(1.f + aspect * aspect);
@@ -691,9 +700,8 @@ int launch_postprocess(float* points, const float* normal_in, const float* mask_
                        float* depth, float* normal_out, uint8_t* mask_out, float* intrinsics, cudaStream_t st) {
     const size_t npix = static_cast<size_t>(H) * W;
     dim3 grid(static_cast<unsigned>(std::min<size_t>((npix + 255) / 256, 148 * 8)), B);
-    postprocess_kernel<<<grid, 256, 0, st>>>(points, normal_in, mask_prob, metric_scale, focal, shift, H, W, force_projection,
-                                             apply_mask, depth, normal_out, mask_out, intrinsics);
-    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(launch_pdl(postprocess_kernel, grid, dim3(256), 0, st, points, normal_in, mask_prob, metric_scale, focal, shift, H, W, force_projection,
+                        apply_mask, depth, normal_out, mask_out, intrinsics));
     return 0;
 }
 

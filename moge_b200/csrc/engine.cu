@@ -1178,6 +1178,11 @@ int moge_engine_forward_groups(moge_engine_t* e, const moge_group_t* groups, int
     // ---- graph replay of the workspace-only launches (small batches only: at large batch the GPU is the bottleneck and the CPU
     //      runs ahead anyway).  The first run of a plan is eager (sets kernel attributes, warms caches).
     const bool want_graph = e->use_graphs && tokens <= 4 * 3600;
+    struct PdlScope {          // programmatic dependent launch for the small calls only (host_api.h)
+        bool prev;
+        explicit PdlScope(bool on) : prev(pdl_scope()) { pdl_scope() = on; }
+        ~PdlScope() { pdl_scope() = prev; }
+    } pdl(tokens <= 4 * 3600);
     if (!want_graph || pl->eager_runs == 0) {
         pl->eager_runs++;
         for (auto& op : pl->ops) MG_TRY(op.fn(st));

@@ -6,6 +6,7 @@
 #include <stddef.h>
 #include <atomic>
 #include <vector>
+#include <utility>
 
 namespace mg {
 
@@ -46,6 +47,27 @@ struct DevOnce {
             _once.mark(_dev);                                                                            \
         }                                                                                                \
     } while (0)
+
+// Programmatic dependent launch (PDL): every kernel of the forward path starts with `pdl_prologue()` (common.cuh:
+// griddepcontrol.launch_dependents, then griddepcontrol.wait) and is launched with programmatic stream serialization, so the NEXT
+// kernel's launch, block scheduling and prologue overlap the tail of this one instead of waiting for the full drain of the grid;
+// correctness is unchanged (the wait returns only when the predecessor grid has completed and flushed).  It matters at batch 1,
+// where a forward is ~245 kernels of a few microseconds each (also inside the captured CUDA graph): measured 3.554 -> 3.515 ms p50.
+// At batch 32 the kernels are long and early-resident dependents only get in the way (same-box A/B: 50.2 -> 51.0 ms per step), so
+// the engine switches it on per call, for the small (graph-replayed) calls only: `pdl_scope` is thread-local state read by
+// `launch_pdl`.  MOGE_B200_PDL=0 disables it altogether.
+bool pdl_enabled();
+bool& pdl_scope();
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = (pdl_enabled() && pdl_scope()) ? 1 : 0;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);
+}
 
 // ---- TMA descriptors (driver entry point resolved at run time; no link-time libcuda dependency)
 // 16-bit element maps with a 64-element (128-byte) inner box and SWIZZLE_128B.

@@ -3,6 +3,7 @@
 #include "host_api.h"
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <mutex>
 
 namespace mg {
@@ -16,6 +17,16 @@ int set_error(const char* fmt, ...) {
     return -1;
 }
 const char* last_error() { return g_err; }
+
+bool& pdl_scope() {
+    static thread_local bool on = false;
+    return on;
+}
+
+bool pdl_enabled() {
+    static const bool on = [] { const char* v = getenv("MOGE_B200_PDL"); return !(v != nullptr && v[0] == '0'); }();
+    return on;
+}
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,

@@ -11,8 +11,7 @@ static int launch_inst(const CUtensorMap& a, const CUtensorMap& b, const UmmaPar
     const int total = ((p.num_m_tiles + 1) / 2) * p.num_n_tiles;
     if (total <= 0) return 0;
     const int pairs = total < num_sms / 2 ? total : num_sms / 2;
-    kern<<<2 * pairs, Umma2Cfg::kThreads, Umma2Cfg::kSmemBytes, st>>>(a, b, p);
-    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(launch_pdl(kern, dim3(2 * pairs), dim3(Umma2Cfg::kThreads), Umma2Cfg::kSmemBytes, st, a, b, p));
     return 0;
 }
 

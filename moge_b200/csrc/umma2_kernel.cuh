@@ -70,6 +70,7 @@ struct Umma2Cfg {
 template <int EPI, bool BF16>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Umma2Cfg::kThreads, 1)
 umma2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const UmmaParams p) {
+    pdl_launch_dependents();      // (the wait sits after the barrier / TMEM set-up below: that prologue overlaps the previous kernel's tail)
     using Cfg = Umma2Cfg;
     constexpr int S = Cfg::kStages;
     constexpr int BN = Cfg::BN;
@@ -102,6 +103,7 @@ umma2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
     cluster_sync_all();                                           // barriers of both CTAs initialised before any remote signal
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_wait();
 
     if (warp == 0) {
         // ================================================================== TMA producer (both CTAs; converged warp, elected lane issues)

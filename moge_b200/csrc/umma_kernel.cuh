@@ -462,16 +462,10 @@ __device__ __forceinline__ void epilogue_tile(const UmmaParams& p, int mt, int n
             const int col = nt * BN + col_begin + c;       // first global output column of this chunk
             int co = col + 4 * q4;                         // this lane's 4 columns
             float4 pre[8];
-            // EPI_RESID (proj / fc2): the fp32 residual reads do not depend on the accumulator -- they are issued FIRST, so that
-            // their HBM latency runs under the TMEM load and the transpose (ncu: these launches stall on long_scoreboard, 7.6 warps
-            // per issue cycle, at 48 % of the DRAM peak: bound by loads in flight, not by bandwidth)
-            if (EPI == EPI_RESID) {
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    pre[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (FULL || ok[i]) pre[i] = *reinterpret_cast<const float4*>(static_cast<const float*>(p.out0) + roff[i] + co);
-                }
-            }
+            // (EPI_RESID -- proj / fc2 -- stalls on the latency of the fp32 residual reads: ncu long_scoreboard 7.6 warps per issue
+            // cycle at 48 % of the DRAM peak.  Issuing those reads HERE, ahead of the TMEM load and the transpose, measured SLOWER in a
+            // same-box A/B -- proj 3.41 -> 3.65 ms per step -- like the two-chunk prefetch before it: the longer live ranges cost
+            // registers / spills in an epilogue that sits at the 168-register cap.  Kept load-then-use.)
             float v[32];
             tmem_ld32(t_addr + c, v);
             tc_wait_ld();
@@ -501,12 +495,12 @@ __device__ __forceinline__ void epilogue_tile(const UmmaParams& p, int mt, int n
             int sY[8], sX[8];
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-                if (EPI != EPI_RESID) pre[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                pre[i] = make_float4(0.f, 0.f, 0.f, 0.f);
                 sY[i] = ry[i]; sX[i] = rx[i];
                 if (EPI == EPI_DEC && shuffle) { sY[i] = 2 * ry[i] + (qd >> 1); sX[i] = 2 * rx[i] + (qd & 1); }
                 if (!FULL && !ok[i]) continue;
                 if (EPI == EPI_RESID) {
-                    // (loaded at the top of the chunk)
+                    pre[i] = *reinterpret_cast<const float4*>(static_cast<const float*>(p.out0) + roff[i] + co);
                 } else if (EPI == EPI_PATCH) {
                     const int t = ry[i] * p.W + rx[i];
                     pre[i] = *reinterpret_cast<const float4*>(p.vec1 + static_cast<size_t>(t) * p.ldo + co);
@@ -621,6 +615,7 @@ template <int BN, int AMODE, int EPI, bool BF16, int DF = -1>
 __global__ void __launch_bounds__(UmmaCfg<BN>::kThreads, 1)
 umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapAux,
             const __grid_constant__ CUtensorMap mapB, const UmmaParams p) {
+    pdl_launch_dependents();      // (the wait sits after the barrier / TMEM set-up below: that prologue overlaps the previous kernel's tail)
     using Cfg = UmmaCfg<BN>;
     using H = H16<BF16>;
     constexpr int S = Cfg::kStages;
@@ -652,6 +647,7 @@ umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_wait();
 
     if (warp == 0) {
         // ================================================================== TMA producer
