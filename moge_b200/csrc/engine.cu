@@ -793,7 +793,6 @@ static int build_plan(moge_engine* e, Plan* pl, bool dry, size_t* bytes_out, cud
     Plan* P = pl;
     const bool fold = e->ln_fold;
     const int sms = e->num_sms;
-    const std::string gsuffix_none;
     auto gname = [&](const char* base, int gi) { return G == 1 ? std::string(base) : std::string(base) + ".g" + std::to_string(gi); };
     // ---- per group: K1 resize + normalise + patchify (phase 0: reads the caller's image), K2/K3 patch embed + pos embed, cls rows
     int parts_x = 0;              // column groups per row of the statistics the NEXT consumer reads

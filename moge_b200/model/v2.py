@@ -65,7 +65,6 @@ class MoGeModel:
         self._engine = None                 # C handle
         self._engine_key = None
         self._workspace: Optional[torch.Tensor] = None
-        self._warned_fp32 = False
         self.training = False
         self.max_chunk_tokens = 48 * 1370          # images per engine call = max_chunk_tokens // (tokens per image)
 

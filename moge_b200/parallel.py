@@ -1,7 +1,10 @@
 """Data-parallel plumbing for the MoGe-2 hot path: images are independent units, so ranks shard
-the batch with NO collective on the data path.  NCCL (torch.distributed) is used for exactly two things:
-one broadcast of the checkpoint tensors from rank 0 at load time, and the gather of the output maps to rank 0.
-One process per GPU (torchrun); works with the gloo backend on CPU tensors for the host-logic tests."""
+the batch with NO collective on the data path.  One process per GPU (torchrun).
+  * `broadcast_state_dict`: one NCCL broadcast of the checkpoint tensors from rank 0 at load time;
+  * `PeerGatherer`: the per-step gather of the output maps to rank 0 over NVLink peer memory (CUDA-IPC staging slots, copy-engine
+    pulls, device-side flags; libmoge_b200's moge_peer_* entry points) -- the product path, no SM time;
+  * `OutputGatherer` / `gather_outputs`: the same gather as NCCL (or gloo) send/recv -- kept for comparison in bench.py and for
+    the world-size-2 gloo tests of the host logic on CPU tensors."""
 from __future__ import annotations
 
 from typing import Dict, List, Optional, Tuple
