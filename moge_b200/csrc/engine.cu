@@ -640,6 +640,17 @@ static int add_linear(moge_engine* e, Plan* pl, const void* A, int M, int K, int
     if (bn == 256 && e->use_2cta && (epi == EPI_STORE16 || epi == EPI_GELU16 || epi == EPI_RESID)) {
         MG_TRY(make_map_2d(&mb, W, K, N, lda, 128));
         double bytes2 = static_cast<double>(M) * K * 2 + static_cast<double>(N) * K * 2 + ((epi == EPI_RESID) ? static_cast<double>(M) * N * 8 : static_cast<double>(M) * N * 2) + ln_extra_bytes;
+        // EPI_RESID with a short reduction (proj: K = D): the fp32 residual is staged through shared memory by TMA, two 32 x 32
+        // chunks per epilogue warp ahead of their use, in place of two of the six ring stages -- same-box A/B: proj 3.38 -> 3.03 ms
+        // per step.  fc2 (K = 4 D) keeps the six-stage ring and reads the residual from global memory: with four stages it loses
+        // more in the main loop than the staging wins (6.93 -> 7.77 ms).  MOGE_B200_RESID_TMA=0 disables the staging.
+        static const bool resid_tma = [] { const char* v = getenv("MOGE_B200_RESID_TMA"); return !(v != nullptr && v[0] == '0'); }();
+        if (epi == EPI_RESID && resid_tma && (N % 32) == 0 && K <= N) {
+            CUtensorMap mr;
+            MG_TRY(make_map_2d_f32(&mr, out, N, M, ldo));
+            pl->ops.add([=](cudaStream_t st) { return launch_umma2(epi, bf16, ma, mb, p, sms, st, &mr); }, name, flops2, bytes2);
+            return 0;
+        }
         pl->ops.add([=](cudaStream_t st) { return launch_umma2(epi, bf16, ma, mb, p, sms, st); }, name, flops2, bytes2);
         return 0;
     }

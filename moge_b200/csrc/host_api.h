@@ -73,6 +73,8 @@ inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, siz
 // 16-bit element maps with a 64-element (128-byte) inner box and SWIZZLE_128B.
 int make_map_2d(CUtensorMap* m, const void* base, uint64_t cols, uint64_t rows, uint64_t row_pitch_elems, uint32_t box_rows);
 int make_map_3d(CUtensorMap* m, const void* base, uint64_t cols, uint64_t rows, uint64_t batch, uint32_t box_rows);
+// fp32 row-major matrix: box {32 columns (128 bytes), 32 rows}, SWIZZLE_128B (the residual stream of the EPI_RESID epilogue)
+int make_map_2d_f32(CUtensorMap* m, const void* base, uint64_t cols, uint64_t rows, uint64_t row_pitch_elems);
 // padded NHWC image [B, Hp, Wp, C]: box {64 ch, 16 px, 8 rows, 1}
 int make_map_nhwc(CUtensorMap* m, const void* base, uint64_t C, uint64_t Wp, uint64_t Hp, uint64_t B, uint32_t box_rows = 8);
 
@@ -82,7 +84,10 @@ int launch_umma(int bn, int amode, int epi, bool bf16, const CUtensorMap& a, con
                 const UmmaParams& p, int num_sms, cudaStream_t st);
 
 // 2-CTA (cta_group::2) encoder GEMM, 256x256 pair tiles; a, b: box {64,128}
-int launch_umma2(int epi, bool bf16, const CUtensorMap& a, const CUtensorMap& b, const UmmaParams& p, int num_sms, cudaStream_t st);
+// `resid`: EPI_RESID only -- fp32 map of the residual matrix (out0); non-null: the epilogue stages the residual through shared memory
+// by TMA (loads run under the MMA main loop) instead of reading it from global memory inside the epilogue
+int launch_umma2(int epi, bool bf16, const CUtensorMap& a, const CUtensorMap& b, const UmmaParams& p, int num_sms, cudaStream_t st,
+                 const CUtensorMap* resid = nullptr);
 // 3x3 conv with C_in = 64: resident weights + 3 halo boxes per tile (conv64_kernel.cuh); a: box {64,16,10}, aux: box {64,16,8}
 int launch_conv64(int bn, int epi, bool bf16, const CUtensorMap& a, const CUtensorMap& aux, const CUtensorMap& w, const UmmaParams& p,
                   int num_sms, cudaStream_t st);

@@ -45,14 +45,14 @@ static EncodeTiledFn get_encode() {
 }
 
 static int encode(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
-                  const cuuint32_t* box) {
+                  const cuuint32_t* box, CUtensorMapDataType dtype = CU_TENSOR_MAP_DATA_TYPE_UINT16) {
     EncodeTiledFn fn = get_encode();
     if (!fn) return set_error("cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)");
     cuuint32_t estr[5] = {1, 1, 1, 1, 1};
     if (reinterpret_cast<uintptr_t>(base) & 15) return set_error("tensor map base %p not 16-byte aligned", base);
     for (int i = 0; i < rank - 1; ++i)
         if (strides_bytes[i] & 15) return set_error("tensor map stride[%d]=%llu not a multiple of 16 bytes", i, (unsigned long long)strides_bytes[i]);
-    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_UINT16, rank, const_cast<void*>(base), dims, strides_bytes, box, estr,
+    CUresult r = fn(m, dtype, rank, const_cast<void*>(base), dims, strides_bytes, box, estr,
                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS)
@@ -68,6 +68,13 @@ int make_map_2d(CUtensorMap* m, const void* base, uint64_t cols, uint64_t rows, 
     cuuint64_t strides[1] = {row_pitch_elems * 2};
     cuuint32_t box[2] = {64, box_rows};
     return encode(m, base, 2, dims, strides, box);
+}
+// fp32 row-major matrix [rows, cols] (pitch in elements): box {32 columns = 128 bytes, 32 rows}, SWIZZLE_128B
+int make_map_2d_f32(CUtensorMap* m, const void* base, uint64_t cols, uint64_t rows, uint64_t row_pitch_elems) {
+    cuuint64_t dims[2] = {cols, rows};
+    cuuint64_t strides[1] = {row_pitch_elems * 4};
+    cuuint32_t box[2] = {32, 32};
+    return encode(m, base, 2, dims, strides, box, CU_TENSOR_MAP_DATA_TYPE_FLOAT32);
 }
 int make_map_3d(CUtensorMap* m, const void* base, uint64_t cols, uint64_t rows, uint64_t batch, uint32_t box_rows) {
     cuuint64_t dims[3] = {cols, rows, batch};

@@ -54,24 +54,31 @@ __device__ __forceinline__ void tmem_dealloc_2sm(uint32_t taddr, uint32_t ncols)
     asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
 }
 
-struct Umma2Cfg {
+// RS: the EPI_RESID residual is staged through shared memory by TMA (two 4 KB chunk buffers per epilogue warp); it takes the
+// place of two ring stages (K = 1024 ... 4096 needs no more than 4 stages to cover the TMA latency).
+template <bool RS> struct Umma2CfgT {
     static constexpr int BN = 256;                          // output columns of the pair tile; each CTA stages 128 of them
     static constexpr int kStageBytes = TILE_M * 128 + 128 * 128;   // A: 128 rows, B: 128 rows (this CTA's half), 64 k each
-    static constexpr int kStages = 6;
+    static constexpr int kStages = RS ? 4 : 6;
     static constexpr int kEpiWarps = 8;
     static constexpr int kThreads = 64 + 32 * kEpiWarps;
     static constexpr int kTmemCols = 512;
     static constexpr int kScratchBytes = kEpiWarps * 4096;
-    static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256 + kScratchBytes;
+    static constexpr int kResidBytes = RS ? kEpiWarps * 2 * 4096 : 0;
+    static constexpr int kBarBytes = 1024;                  // full/empty rings, accumulator barriers, residual barriers, TMEM slot (keeps what follows 1024-byte aligned)
+    static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + kBarBytes + kScratchBytes + kResidBytes;
     static_assert(kSmemBytes <= kMaxDynSmem, "umma2_kernel: stage ring + scratch exceed the shared memory of one CTA");
-    static_assert((2 * kStages + 4) * 8 + 4 <= 256, "umma2_kernel: barrier block overflows its 256 bytes");
+    static_assert((2 * kStages + 4 + 2 * kEpiWarps) * 8 + 4 <= kBarBytes, "umma2_kernel: barrier block overflows");
 };
+using Umma2Cfg = Umma2CfgT<false>;
 
-template <int EPI, bool BF16>
+template <int EPI, bool BF16, bool RS = false>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Umma2Cfg::kThreads, 1)
-umma2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const UmmaParams p) {
+umma2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const __grid_constant__ CUtensorMap mapR,
+             const UmmaParams p) {
+    static_assert(!RS || EPI == EPI_RESID, "the staged residual belongs to EPI_RESID");
     pdl_launch_dependents();      // (the wait sits after the barrier / TMEM set-up below: that prologue overlaps the previous kernel's tail)
-    using Cfg = Umma2Cfg;
+    using Cfg = Umma2CfgT<RS>;
     constexpr int S = Cfg::kStages;
     constexpr int BN = Cfg::BN;
     extern __shared__ uint8_t smem_raw[];
@@ -80,8 +87,10 @@ umma2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
     uint64_t* empty = full + S;
     uint64_t* tfull = empty + S;
     uint64_t* tempty = tfull + 2;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
-    float* scratch_base = reinterpret_cast<float*>(smem + S * Cfg::kStageBytes + 256);
+    uint64_t* rfull = tempty + 2;                              // RS: [epilogue warp][2 buffers]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(rfull + 2 * Cfg::kEpiWarps);
+    float* scratch_base = reinterpret_cast<float*>(smem + S * Cfg::kStageBytes + Cfg::kBarBytes);
+    uint8_t* resid_base = smem + S * Cfg::kStageBytes + Cfg::kBarBytes + Cfg::kScratchBytes;     // 1024-byte aligned (all terms are)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = cluster_ctarank();
@@ -96,6 +105,7 @@ umma2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
         tma_prefetch_desc(&mapB);
         for (int s = 0; s < S; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
         for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 2 * Cfg::kEpiWarps); }
+        if (RS) { tma_prefetch_desc(&mapR); for (int i = 0; i < 2 * Cfg::kEpiWarps; ++i) mbar_init(&rfull[i], 1); }
         fence_mbar_init();
     }
     if (warp == 1) tmem_alloc_2sm(tmem_slot, Cfg::kTmemCols);
@@ -166,6 +176,24 @@ umma2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
         LnRows lnr{}, lnn{};
         const bool ln_on = (EPI == EPI_STORE16 || EPI == EPI_GELU16) && p.ln_rstd != nullptr;
         if (ln_on && pair < total) ln_load(p, 2 * (pair / p.num_n_tiles) + static_cast<int>(rank), quarter, lane, lnn);
+        // RS: the fp32 residual of this warp's 32 rows x 128 columns arrives in 32 x 32 chunks by TMA, two chunks ahead of their use;
+        // the first two chunks of a tile are requested while the previous tile is still being drained, i.e. they land under the
+        // MMA main loop instead of stalling the epilogue (proj / fc2 were bound by the latency of these reads).
+        ResidPipe rp{};
+        if (RS) {
+            rp.buf = resid_base + ew * 8192; rp.bars = rfull + 2 * ew; rp.map = &mapR; rp.rc = 0;
+            if (pair < total) {
+                const int row0 = (2 * (pair / p.num_n_tiles) + static_cast<int>(rank)) * TILE_M + quarter * 32;
+                const int col0 = (pair % p.num_n_tiles) * BN + col_begin;
+                if (elect_one()) {
+                    for (int b = 0; b < 2; ++b) {
+                        mbar_arrive_expect_tx(&rp.bars[b], 4096);
+                        tma_load_2d(rp.buf + b * 4096, &mapR, &rp.bars[b], col0 + 32 * b, row0);
+                    }
+                }
+                __syncwarp();
+            }
+        }
         for (int t = pair; t < total; t += npairs, ++it) {
             const int mp = t / p.num_n_tiles, nt = t % p.num_n_tiles;
             const int mt = 2 * mp + static_cast<int>(rank);
@@ -174,10 +202,15 @@ umma2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
                 lnr = lnn;
                 if (t + npairs < total) ln_load(p, 2 * ((t + npairs) / p.num_n_tiles) + static_cast<int>(rank), quarter, lane, lnn);
             }
+            if (RS) {
+                const int tn = t + npairs;
+                rp.next_row0 = (tn < total) ? (2 * (tn / p.num_n_tiles) + static_cast<int>(rank)) * TILE_M + quarter * 32 : -1;
+                rp.next_col0 = (tn < total) ? (tn % p.num_n_tiles) * BN + col_begin : 0;
+            }
             mbar_wait(&tfull[acc], (it >> 1) & 1);
             tc_fence_after();
             const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN + col_begin;
-            epilogue_tile<BN, BN / 2, AMODE_ROWS, EPI, BF16>(p, mt, nt, t_addr, scr, quarter, lane, col_begin, ln_on, lnr);
+            epilogue_tile<BN, BN / 2, AMODE_ROWS, EPI, BF16>(p, mt, nt, t_addr, scr, quarter, lane, col_begin, ln_on, lnr, RS ? &rp : nullptr);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) {

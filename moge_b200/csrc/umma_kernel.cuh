@@ -143,6 +143,16 @@ __device__ __forceinline__ void ln_load(const UmmaParams& p, int mt, int quarter
     }
 }
 
+// EPI_RESID with the residual staged by TMA (umma2_kernel): per epilogue warp two 32 x 32 fp32 chunk buffers (128-byte rows,
+// SWIZZLE_128B) and their mbarriers; `rc` counts the chunks this warp has consumed (buffer = rc & 1, phase = (rc >> 1) & 1).
+struct ResidPipe {
+    uint8_t* buf;                 // 2 x 4096 bytes, 1024-byte aligned
+    uint64_t* bars;               // 2 mbarriers
+    const CUtensorMap* map;       // fp32 [M, N], box {32, 32}
+    uint32_t rc;
+    int next_row0, next_col0;     // first row / first column (of this warp's column group) of the NEXT tile, next_row0 < 0: none
+};
+
 // DF < 0: the EPI_DEC variant (raw / ReLU copies, skip, UV, pixel shuffle) is decided at run time from the params;
 // DF >= 0: compile-time bit mask (DF_RAW | DF_RELU | DF_SKIP | DF_UV | DF_SHUFFLE) -- a much smaller hot loop.
 enum : int { DF_RAW = 1, DF_RELU = 2, DF_SKIP = 4, DF_UV = 8, DF_SHUFFLE = 16 };
@@ -306,7 +316,8 @@ __device__ __forceinline__ void epilogue_dec16(const UmmaParams& p, int mt, int 
 
 template <int BN, int COLS, int AMODE, int EPI, bool BF16, int DF = -1>
 __device__ __forceinline__ void epilogue_tile(const UmmaParams& p, int mt, int nt, uint32_t t_addr, float4* scr, int quarter,
-                                              int lane, int col_begin, bool ln_rows_on = false, LnRows lnr = LnRows{}) {
+                                              int lane, int col_begin, bool ln_rows_on = false, LnRows lnr = LnRows{},
+                                              ResidPipe* rp = nullptr) {
     using H = H16<BF16>;
     const bool has_raw = (DF < 0) ? (p.out0 != nullptr) : ((DF & DF_RAW) != 0);
     const bool has_relu = (DF < 0) ? (p.out1 != nullptr) : ((DF & DF_RELU) != 0);
@@ -500,7 +511,7 @@ __device__ __forceinline__ void epilogue_tile(const UmmaParams& p, int mt, int n
                 if (EPI == EPI_DEC && shuffle) { sY[i] = 2 * ry[i] + (qd >> 1); sX[i] = 2 * rx[i] + (qd & 1); }
                 if (!FULL && !ok[i]) continue;
                 if (EPI == EPI_RESID) {
-                    pre[i] = *reinterpret_cast<const float4*>(static_cast<const float*>(p.out0) + roff[i] + co);
+                    if (rp == nullptr) pre[i] = *reinterpret_cast<const float4*>(static_cast<const float*>(p.out0) + roff[i] + co);
                 } else if (EPI == EPI_PATCH) {
                     const int t = ry[i] * p.W + rx[i];
                     pre[i] = *reinterpret_cast<const float4*>(p.vec1 + static_cast<size_t>(t) * p.ldo + co);
@@ -509,6 +520,30 @@ __device__ __forceinline__ void epilogue_tile(const UmmaParams& p, int mt, int n
                     const float2 f0 = H::unpack(u.x), f1 = H::unpack(u.y);
                     pre[i] = make_float4(f0.x, f0.y, f1.x, f1.y);
                 }
+            }
+            if (EPI == EPI_RESID && rp != nullptr) {
+                // residual chunk from the TMA-staged buffer: row rl = 4 i + sub is one swizzled 128-byte line, this lane's 4 columns
+                // are its 16-byte chunk q4 ^ (rl & 7)
+                const uint32_t b = rp->rc & 1u;
+                mbar_wait(&rp->bars[b], (rp->rc >> 1) & 1u);
+                const uint8_t* rb_ = rp->buf + b * 4096;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int rl = 4 * i + sub;
+                    pre[i] = *reinterpret_cast<const float4*>(rb_ + rl * 128 + ((q4 ^ (rl & 7)) << 4));
+                }
+                fence_proxy_async_smem();           // these generic-proxy reads are ordered before the TMA write that refills the buffer
+                __syncwarp();
+                // refill the buffer: chunk c + 64 of this tile, or the first chunks of the next tile (they land under its main loop)
+                int ncol = -1, nrow = 0;
+                if (c + 64 < COLS) { ncol = nt * BN + col_begin + c + 64; nrow = mt * TILE_M + quarter * 32; }
+                else if (rp->next_row0 >= 0) { ncol = rp->next_col0 + (c + 64 - COLS); nrow = rp->next_row0; }
+                if (ncol >= 0 && elect_one()) {
+                    mbar_arrive_expect_tx(&rp->bars[b], 4096);
+                    tma_load_2d(rp->buf + b * 4096, rp->map, &rp->bars[b], ncol, nrow);
+                }
+                __syncwarp();
+                rp->rc++;
             }
             // ---- phase 2: math + stores
             uint2 pk_raw[8], pk_relu[8];
