@@ -645,10 +645,12 @@ static int add_linear(moge_engine* e, Plan* pl, const void* A, int M, int K, int
         // per step.  fc2 (K = 4 D) keeps the six-stage ring and reads the residual from global memory: with four stages it loses
         // more in the main loop than the staging wins (6.93 -> 7.77 ms).  MOGE_B200_RESID_TMA=0 disables the staging.
         static const bool resid_tma = [] { const char* v = getenv("MOGE_B200_RESID_TMA"); return !(v != nullptr && v[0] == '0'); }();
-        if (epi == EPI_RESID && resid_tma && (N % 32) == 0 && K <= N) {
+        static const bool resid_tma_long = [] { const char* v = getenv("MOGE_B200_RESID_TMA_LONGK"); return v != nullptr && v[0] == '1'; }();
+        if (epi == EPI_RESID && resid_tma && (N % 32) == 0 && (K <= N || resid_tma_long)) {
             CUtensorMap mr;
             MG_TRY(make_map_2d_f32(&mr, out, N, M, ldo));
-            pl->ops.add([=](cudaStream_t st) { return launch_umma2(epi, bf16, ma, mb, p, sms, st, &mr); }, name, flops2, bytes2);
+            const int nbuf = (K <= N) ? 2 : 1;
+            pl->ops.add([=](cudaStream_t st) { return launch_umma2(epi, bf16, ma, mb, p, sms, st, &mr, nbuf); }, name, flops2, bytes2);
             return 0;
         }
         pl->ops.add([=](cudaStream_t st) { return launch_umma2(epi, bf16, ma, mb, p, sms, st); }, name, flops2, bytes2);

@@ -87,7 +87,7 @@ int launch_umma(int bn, int amode, int epi, bool bf16, const CUtensorMap& a, con
 // `resid`: EPI_RESID only -- fp32 map of the residual matrix (out0); non-null: the epilogue stages the residual through shared memory
 // by TMA (loads run under the MMA main loop) instead of reading it from global memory inside the epilogue
 int launch_umma2(int epi, bool bf16, const CUtensorMap& a, const CUtensorMap& b, const UmmaParams& p, int num_sms, cudaStream_t st,
-                 const CUtensorMap* resid = nullptr);
+                 const CUtensorMap* resid = nullptr, int resid_bufs = 2);
 // 3x3 conv with C_in = 64: resident weights + 3 halo boxes per tile (conv64_kernel.cuh); a: box {64,16,10}, aux: box {64,16,8}
 int launch_conv64(int bn, int epi, bool bf16, const CUtensorMap& a, const CUtensorMap& aux, const CUtensorMap& w, const UmmaParams& p,
                   int num_sms, cudaStream_t st);

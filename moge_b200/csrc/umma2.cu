@@ -4,7 +4,7 @@
 
 namespace mg {
 
-template <int EPI, bool BF16, bool RS = false>
+template <int EPI, bool BF16, int RS = 0>
 static int launch_inst(const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& r, const UmmaParams& p, int num_sms, cudaStream_t st) {
     auto kern = umma2_kernel<EPI, BF16, RS>;
     MG_SET_SMEM_ONCE(kern, Umma2CfgT<RS>::kSmemBytes);
@@ -17,10 +17,12 @@ static int launch_inst(const CUtensorMap& a, const CUtensorMap& b, const CUtenso
 
 // a: box {64,128}; b: box {64,128} (each CTA of the pair stages half of the 256-column tile); p.num_n_tiles = N / 256.
 int launch_umma2(int epi, bool bf16, const CUtensorMap& a, const CUtensorMap& b, const UmmaParams& p, int num_sms, cudaStream_t st,
-                 const CUtensorMap* resid) {
+                 const CUtensorMap* resid, int resid_bufs) {
     if (p.N % 256) return set_error("umma2: N=%d must be a multiple of 256", p.N);
-    if (epi == EPI_RESID && resid != nullptr)
-        return bf16 ? launch_inst<EPI_RESID, true, true>(a, b, *resid, p, num_sms, st) : launch_inst<EPI_RESID, false, true>(a, b, *resid, p, num_sms, st);
+    if (epi == EPI_RESID && resid != nullptr && resid_bufs == 2)
+        return bf16 ? launch_inst<EPI_RESID, true, 2>(a, b, *resid, p, num_sms, st) : launch_inst<EPI_RESID, false, 2>(a, b, *resid, p, num_sms, st);
+    if (epi == EPI_RESID && resid != nullptr && resid_bufs == 1)
+        return bf16 ? launch_inst<EPI_RESID, true, 1>(a, b, *resid, p, num_sms, st) : launch_inst<EPI_RESID, false, 1>(a, b, *resid, p, num_sms, st);
 #define INST(EPI)                                                                                     \
     if (epi == EPI) return bf16 ? launch_inst<EPI, true>(a, b, a, p, num_sms, st) : launch_inst<EPI, false>(a, b, a, p, num_sms, st);
     INST(EPI_STORE16) INST(EPI_GELU16) INST(EPI_RESID)

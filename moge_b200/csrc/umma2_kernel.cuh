@@ -54,29 +54,29 @@ __device__ __forceinline__ void tmem_dealloc_2sm(uint32_t taddr, uint32_t ncols)
     asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
 }
 
-// RS: the EPI_RESID residual is staged through shared memory by TMA (two 4 KB chunk buffers per epilogue warp); it takes the
-// place of two ring stages (K = 1024 ... 4096 needs no more than 4 stages to cover the TMA latency).
-template <bool RS> struct Umma2CfgT {
+// RS > 0: the EPI_RESID residual is staged through shared memory by TMA (RS 4 KB chunk buffers per epilogue warp, 32 KB per
+// buffer set = one ring stage each): RS = 2 for the short reductions (proj), RS = 1 where the main loop needs the ring (fc2).
+template <int RS> struct Umma2CfgT {
     static constexpr int BN = 256;                          // output columns of the pair tile; each CTA stages 128 of them
     static constexpr int kStageBytes = TILE_M * 128 + 128 * 128;   // A: 128 rows, B: 128 rows (this CTA's half), 64 k each
-    static constexpr int kStages = RS ? 4 : 6;
+    static constexpr int kStages = 6 - RS;                  // RS = number of 4 KB residual chunk buffers per epilogue warp (0, 1 or 2)
     static constexpr int kEpiWarps = 8;
     static constexpr int kThreads = 64 + 32 * kEpiWarps;
     static constexpr int kTmemCols = 512;
     static constexpr int kScratchBytes = kEpiWarps * 4096;
-    static constexpr int kResidBytes = RS ? kEpiWarps * 2 * 4096 : 0;
+    static constexpr int kResidBytes = kEpiWarps * RS * 4096;
     static constexpr int kBarBytes = 1024;                  // full/empty rings, accumulator barriers, residual barriers, TMEM slot (keeps what follows 1024-byte aligned)
     static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + kBarBytes + kScratchBytes + kResidBytes;
     static_assert(kSmemBytes <= kMaxDynSmem, "umma2_kernel: stage ring + scratch exceed the shared memory of one CTA");
     static_assert((2 * kStages + 4 + 2 * kEpiWarps) * 8 + 4 <= kBarBytes, "umma2_kernel: barrier block overflows");
 };
-using Umma2Cfg = Umma2CfgT<false>;
+using Umma2Cfg = Umma2CfgT<0>;
 
-template <int EPI, bool BF16, bool RS = false>
+template <int EPI, bool BF16, int RS = 0>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Umma2Cfg::kThreads, 1)
 umma2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const __grid_constant__ CUtensorMap mapR,
              const UmmaParams p) {
-    static_assert(!RS || EPI == EPI_RESID, "the staged residual belongs to EPI_RESID");
+    static_assert(RS == 0 || EPI == EPI_RESID, "the staged residual belongs to EPI_RESID");
     pdl_launch_dependents();      // (the wait sits after the barrier / TMEM set-up below: that prologue overlaps the previous kernel's tail)
     using Cfg = Umma2CfgT<RS>;
     constexpr int S = Cfg::kStages;
@@ -181,12 +181,12 @@ umma2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
         // MMA main loop instead of stalling the epilogue (proj / fc2 were bound by the latency of these reads).
         ResidPipe rp{};
         if (RS) {
-            rp.buf = resid_base + ew * 8192; rp.bars = rfull + 2 * ew; rp.map = &mapR; rp.rc = 0;
+            rp.buf = resid_base + ew * (RS * 4096); rp.bars = rfull + 2 * ew; rp.map = &mapR; rp.rc = 0; rp.nbuf = RS;
             if (pair < total) {
                 const int row0 = (2 * (pair / p.num_n_tiles) + static_cast<int>(rank)) * TILE_M + quarter * 32;
                 const int col0 = (pair % p.num_n_tiles) * BN + col_begin;
                 if (elect_one()) {
-                    for (int b = 0; b < 2; ++b) {
+                    for (int b = 0; b < RS; ++b) {
                         mbar_arrive_expect_tx(&rp.bars[b], 4096);
                         tma_load_2d(rp.buf + b * 4096, &mapR, &rp.bars[b], col0 + 32 * b, row0);
                     }

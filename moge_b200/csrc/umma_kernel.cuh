@@ -150,6 +150,7 @@ struct ResidPipe {
     uint64_t* bars;               // 2 mbarriers
     const CUtensorMap* map;       // fp32 [M, N], box {32, 32}
     uint32_t rc;
+    int nbuf;                     // 1 or 2 chunk buffers
     int next_row0, next_col0;     // first row / first column (of this warp's column group) of the NEXT tile, next_row0 < 0: none
 };
 
@@ -524,8 +525,8 @@ __device__ __forceinline__ void epilogue_tile(const UmmaParams& p, int mt, int n
             if (EPI == EPI_RESID && rp != nullptr) {
                 // residual chunk from the TMA-staged buffer: row rl = 4 i + sub is one swizzled 128-byte line, this lane's 4 columns
                 // are its 16-byte chunk q4 ^ (rl & 7)
-                const uint32_t b = rp->rc & 1u;
-                mbar_wait(&rp->bars[b], (rp->rc >> 1) & 1u);
+                const uint32_t b = (rp->nbuf == 2) ? (rp->rc & 1u) : 0u;
+                mbar_wait(&rp->bars[b], ((rp->nbuf == 2) ? (rp->rc >> 1) : rp->rc) & 1u);
                 const uint8_t* rb_ = rp->buf + b * 4096;
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
@@ -534,10 +535,12 @@ __device__ __forceinline__ void epilogue_tile(const UmmaParams& p, int mt, int n
                 }
                 fence_proxy_async_smem();           // these generic-proxy reads are ordered before the TMA write that refills the buffer
                 __syncwarp();
-                // refill the buffer: chunk c + 64 of this tile, or the first chunks of the next tile (they land under its main loop)
+                // refill the buffer `nbuf` chunks ahead: a later chunk of this tile, or the first chunk(s) of the next tile (they land
+                // under its main loop)
+                const int ahead = 32 * rp->nbuf;
                 int ncol = -1, nrow = 0;
-                if (c + 64 < COLS) { ncol = nt * BN + col_begin + c + 64; nrow = mt * TILE_M + quarter * 32; }
-                else if (rp->next_row0 >= 0) { ncol = rp->next_col0 + (c + 64 - COLS); nrow = rp->next_row0; }
+                if (c + ahead < COLS) { ncol = nt * BN + col_begin + c + ahead; nrow = mt * TILE_M + quarter * 32; }
+                else if (rp->next_row0 >= 0) { ncol = rp->next_col0 + (c + ahead - COLS); nrow = rp->next_row0; }
                 if (ncol >= 0 && elect_one()) {
                     mbar_arrive_expect_tx(&rp->bars[b], 4096);
                     tma_load_2d(rp->buf + b * 4096, rp->map, &rp->bars[b], ncol, nrow);
