@@ -111,6 +111,14 @@ int moge_engine_num_ops(moge_engine_t* e, int* n);
 int moge_engine_op_info(moge_engine_t* e, int idx, char* name, int name_cap, double* flops, double* bytes);
 int moge_engine_profile(moge_engine_t* e, float* ms_per_op, int cap, void* stream);
 
+/* host only (no device work): the work list the engine builds at plan time for the persistent attention kernel.
+ * n_tokens[n_images] = token rows per image (class token + patches).  One item = (first row of the image, its token
+ * count, first query row, head) = one 256-query tile of one head; ranges[c] = [begin, end) of the items CTA c walks
+ * (contiguous, cost-balanced, every CTA at least one item; n_ranges = min(n_ctas, n_items)).  items: 4 ints per item,
+ * ranges: 2 ints per CTA (cap n_ctas); either may be NULL to query the counts only.                                     */
+int moge_attention_work_list(const int* n_tokens, int n_images, int heads, int n_ctas, int* items, int items_cap, int* ranges,
+                             int* n_items, int* n_ranges);
+
 /* replaces recover_focal_shift (moge/utils/geometry_torch.py:115-170 + geometry_numpy.py:79-112; SciPy LM on the
  * host in the reference).  points (B,H,W,3) fp32.  Mask: mask_u8 (B,H,W) if non-NULL, else mask_prob > 0.5 if
  * non-NULL, else all valid.  focal_in: NULL (solve focal and shift) or (B,) known focal (solve shift only).      */

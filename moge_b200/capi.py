@@ -21,7 +21,7 @@ RESAMPLE = {"conv_transpose": 0, "bilinear": 1}
 EXPORTS = [
     "moge_last_error", "moge_version", "moge_engine_create", "moge_engine_destroy", "moge_engine_set_weight",
     "moge_engine_finalize", "moge_engine_workspace_bytes", "moge_engine_forward", "moge_engine_workspace_bytes_groups",
-    "moge_engine_forward_groups", "moge_engine_num_ops", "moge_engine_op_info", "moge_engine_profile", "moge_recover_focal_shift",
+    "moge_engine_forward_groups", "moge_engine_num_ops", "moge_engine_op_info", "moge_engine_profile", "moge_attention_work_list", "moge_recover_focal_shift",
     "moge_postprocess", "moge_peer_alloc", "moge_peer_free", "moge_peer_open", "moge_peer_close", "moge_peer_copy", "moge_peer_flag_set",
     "moge_peer_flag_wait", "moge_op_linear", "moge_op_linear_ln", "moge_op_attention", "moge_op_layernorm", "moge_op_conv",
 ]
@@ -84,6 +84,7 @@ def lib() -> C.CDLL:
     L.moge_engine_workspace_bytes_groups.argtypes = [vp, C.POINTER(Group), ci, C.POINTER(C.c_size_t)]
     L.moge_engine_forward_groups.argtypes = [vp, C.POINTER(Group), ci, vp, C.c_size_t, vp]
     L.moge_engine_num_ops.argtypes = [vp, C.POINTER(ci)]
+    L.moge_attention_work_list.argtypes = [C.POINTER(ci), ci, ci, ci, C.POINTER(ci), ci, C.POINTER(ci), C.POINTER(ci), C.POINTER(ci)]
     L.moge_engine_op_info.argtypes = [vp, ci, C.c_char_p, ci, C.POINTER(C.c_double), C.POINTER(C.c_double)]
     L.moge_engine_profile.argtypes = [vp, C.POINTER(C.c_float), ci, vp]
     L.moge_recover_focal_shift.argtypes = [vp, vp, vp, ci, ci, ci, vp, vp, vp, vp]

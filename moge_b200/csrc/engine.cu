@@ -1349,6 +1349,29 @@ int moge_op_attention(const void* qkv, void* out, int B, int N, int D, int heads
     return rc;
 }
 
+int moge_attention_work_list(const int* n_tokens, int n_images, int heads, int n_ctas, int* items, int items_cap, int* ranges, int* n_items,
+                             int* n_ranges) {
+    // host only: the work list the engine uploads for the persistent attention kernel (plan time), for inspection and tests
+    if (n_images < 0 || heads <= 0 || n_ctas <= 0 || !n_tokens) return set_error("attention_work_list: bad arguments");
+    std::vector<int> row0(n_images);
+    int r = 0;
+    for (int i = 0; i < n_images; ++i) {
+        if (n_tokens[i] <= 0) return set_error("attention_work_list: image %d has %d tokens", i, n_tokens[i]);
+        row0[i] = r; r += n_tokens[i];
+    }
+    std::vector<AttnItem> it;
+    std::vector<int2> rg;
+    attention_work_list(row0.data(), n_tokens, n_images, heads, n_ctas, &it, &rg);
+    if (n_items) *n_items = static_cast<int>(it.size());
+    if (n_ranges) *n_ranges = static_cast<int>(rg.size());
+    if (items) {
+        if (items_cap < static_cast<int>(it.size())) return set_error("attention_work_list: items_cap %d < %zu", items_cap, it.size());
+        for (size_t i = 0; i < it.size(); ++i) { items[4 * i] = it[i].row0; items[4 * i + 1] = it[i].n; items[4 * i + 2] = it[i].q0; items[4 * i + 3] = it[i].head; }
+    }
+    if (ranges) for (size_t i = 0; i < rg.size(); ++i) { ranges[2 * i] = rg[i].x; ranges[2 * i + 1] = rg[i].y; }
+    return 0;
+}
+
 int moge_op_linear_ln(const float* x, const float* ln_gamma, const float* ln_beta, const float* w, const float* bias, void* out, int M,
                       int N, int K, int epi, int dtype, void* stream) {
     // out = epi(LayerNorm(x) W^T + bias) the way the engine computes it: rounded rows + row statistics, folded weights, one GEMM

@@ -180,3 +180,67 @@ def test_all_committed_profile_json_files_parse():
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     for f in glob.glob(os.path.join(root, "profiles", "*.json")):
         json.load(open(f))
+
+
+def _work_list(n_tokens, heads, n_ctas):
+    L = capi.lib()
+    n = (C.c_int * len(n_tokens))(*n_tokens)
+    ni, nr = C.c_int(), C.c_int()
+    capi.check(L.moge_attention_work_list(n, len(n_tokens), heads, n_ctas, None, 0, None, C.byref(ni), C.byref(nr)))
+    items = (C.c_int * (4 * max(ni.value, 1)))()
+    ranges = (C.c_int * (2 * n_ctas))()
+    capi.check(L.moge_attention_work_list(n, len(n_tokens), heads, n_ctas, items, ni.value, ranges, C.byref(ni), C.byref(nr)))
+    it = [tuple(items[4 * i:4 * i + 4]) for i in range(ni.value)]
+    rg = [tuple(ranges[2 * i:2 * i + 2]) for i in range(nr.value)]
+    return it, rg
+
+
+@pytest.mark.parametrize("n_tokens,heads,n_ctas", [
+    ([1370] * 32, 16, 148),                  # the benchmark batch
+    ([1370], 16, 148),                       # batch 1: fewer items than CTAs
+    ([3601] * 8, 16, 148),                   # API-default grid
+    ([704, 1370, 704, 3601, 1226, 1370], 12, 148),   # mixed-shape batch (shape groups)
+    ([1], 6, 148), ([256, 257, 512, 513], 6, 7), ([129] * 5, 16, 1),
+])
+def test_attention_work_list_partition(n_tokens, heads, n_ctas):
+    """Plan-time host logic of the persistent attention kernel (attention.cu attention_work_list): every (image, head, 256-query
+    tile) exactly once, the per-CTA ranges contiguous and non-empty, the modelled cost balanced."""
+    it, rg = _work_list(n_tokens, heads, n_ctas)
+    row0 = [sum(n_tokens[:i]) for i in range(len(n_tokens))]
+    want = {(row0[i], n_tokens[i], q0, h) for i in range(len(n_tokens)) for h in range(heads) for q0 in range(0, n_tokens[i], 256)}
+    assert len(it) == len(want) and set(it) == want
+    assert len(rg) == min(n_ctas, len(it))
+    assert rg[0][0] == 0 and rg[-1][1] == len(it)
+    for (b0, e0), (b1, e1) in zip(rg, rg[1:]):
+        assert e0 == b1
+    assert all(e > b for b, e in rg)
+    # cost model of the kernel: kv tiles x query groups per item (+ a constant); no CTA above mean + one largest item
+    cost = [-(-n // 128) * (2 if q0 + 128 < n else 1) + 0.5 for (_, n, q0, _) in it]
+    per_cta = [sum(cost[b:e]) for b, e in rg]
+    assert max(per_cta) <= sum(cost) / len(rg) + max(cost) + 1e-9
+
+
+def test_attention_work_list_rejects_bad_arguments():
+    L = capi.lib()
+    n = (C.c_int * 2)(1370, 0)
+    ni = C.c_int()
+    assert L.moge_attention_work_list(n, 2, 16, 148, None, 0, None, C.byref(ni), None) != 0
+    assert b"tokens" in L.moge_last_error()
+    n = (C.c_int * 1)(1370)
+    items = (C.c_int * 4)()
+    assert L.moge_attention_work_list(n, 1, 16, 148, items, 1, None, C.byref(ni), None) != 0      # items_cap too small
+
+
+@pytest.mark.parametrize("compiler,std,lang", [("gcc", "-std=c99", "c"), ("g++", "-std=c++11", "c++")])
+def test_header_is_plain_c_and_cxx(tmp_path, compiler, std, lang):
+    """The drop-in boundary is a C ABI: include/moge_b200.h must compile as strict C99 and as C++ with nothing but the standard headers."""
+    import shutil
+    import subprocess
+    if shutil.which(compiler) is None:
+        pytest.skip(compiler + " not installed")
+    src = tmp_path / "use_header.c"
+    src.write_text('#include "moge_b200.h"\nint main(void) { moge_config_t c; moge_group_t g; (void)c; (void)g; return moge_version() == 0; }\n')
+    inc = os.path.join(os.path.dirname(capi._HERE), "include")
+    r = subprocess.run([compiler, std, "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", inc, "-x", lang, "-fsyntax-only", str(src)],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
