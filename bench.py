@@ -325,9 +325,9 @@ def run_engine(a):
     ms_e2e = timed(step_pipe, a.steps, fence=pipe.fence)
 
     # ---- BASELINE.json configs[3] as defined: "inputs resident on each GPU -> all outputs resident on rank 0".  Every step ends
-    #      with a gather of the five output maps to rank 0 over NCCL (one grouped isend/irecv batch into preallocated full-batch
-    #      buffers, parallel.OutputGatherer) on a side stream, so the transfer of step i runs under the compute of step i+1; the
-    #      timed region ends when the LAST step's outputs are on rank 0.  At N > 1 this is the line's `value`.
+    #      with a gather of the five output maps into preallocated full-batch buffers on rank 0 (peer-memory pulls, PeerGatherer;
+    #      the NCCL isend/irecv form, OutputGatherer, is timed beside it), so the transfer of step i runs under the compute of
+    #      step i+1; the timed region ends when the LAST step's outputs are on rank 0.  At N > 1 this is the line's `value`.
     gather = None
     ms_gather = None
     if world > 1:
@@ -347,21 +347,29 @@ def run_engine(a):
 
         # (a) product path: peer-memory gather -- IPC-mapped staging slots pulled by rank 0's copy engines, device-side flags,
         #     no SM time (moge_b200.parallel.PeerGatherer over libmoge_b200's moge_peer_* entry points)
-        gat = parallel.PeerGatherer([B] * world, dev)
-        ms_gather, ms_gather_serial = run_gather(gat)
+        gat, peer_error = parallel.PeerGatherer([B] * world, dev), None
+        try:
+            ms_gather, ms_gather_serial = run_gather(gat)
+        except parallel.PeerSetupError as ex:          # raised on every rank together (no CUDA IPC / peer access on this box)
+            gat, peer_error = None, str(ex)
         # (b) for comparison: the same gather as grouped NCCL isend/irecv on a side stream (copy kernels on both ends)
         gat_nccl = parallel.OutputGatherer([B] * world, device=dev)
         ms_nccl, ms_nccl_serial = run_gather(gat_nccl)
+        nccl_api = "moge_b200.parallel.OutputGatherer (grouped NCCL isend/irecv on a side stream)"
+        if gat is None:                                # fall back: the NCCL gather is the measured path of this run
+            ms_gather, ms_gather_serial = ms_nccl, ms_nccl_serial
         gather = {"bytes_to_rank0_per_step": d2h_bytes * (world - 1), "ms_per_step_pipelined": ms_gather / a.steps,
                   "ms_per_step_serial": ms_gather_serial / a.steps, "ms_per_step_no_gather": ms_dev / a.steps,
-                  "api": "moge_b200.parallel.PeerGatherer.submit(infer(...)) per step, fence() at the end: CUDA-IPC staging slots, "
-                         "copy-engine pulls by rank 0, device-side flags; no SM time",
+                  "api": ("moge_b200.parallel.PeerGatherer.submit(infer(...)) per step, fence() at the end: CUDA-IPC staging slots, "
+                          "copy-engine pulls by rank 0, device-side flags; no SM time") if gat is not None
+                         else nccl_api + " -- fallback: " + peer_error,
                   "nccl_isend_irecv": {"ms_per_step_pipelined": ms_nccl / a.steps, "ms_per_step_serial": ms_nccl_serial / a.steps,
-                                       "api": "moge_b200.parallel.OutputGatherer (grouped NCCL isend/irecv on a side stream)"}}
-        if gat.debug:
-            gather["debug_ms"] = gat.debug_report()
-            print(f"[rank {rank}] gather debug (ms): {gather['debug_ms']}", file=sys.stderr, flush=True)
-        gat.close()
+                                       "api": nccl_api}}
+        if gat is not None:
+            if gat.debug:
+                gather["debug_ms"] = gat.debug_report()
+                print(f"[rank {rank}] gather debug (ms): {gather['debug_ms']}", file=sys.stderr, flush=True)
+            gat.close()
 
     if rank != 0:
         if world > 1:

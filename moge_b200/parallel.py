@@ -166,6 +166,10 @@ class OutputGatherer:
             torch.cuda.current_stream(self.device).synchronize()
 
 
+class PeerSetupError(RuntimeError):
+    """PeerGatherer could not allocate / map its CUDA-IPC staging memory on some rank; raised on EVERY rank of the group."""
+
+
 class PeerGatherer:
     """The output gather of BASELINE.json configs[3] over NVLink peer memory, with ZERO SM time (libmoge_b200's moge_peer_* entry
     points): every rank copies its step outputs into an IPC-exported staging slot and raises a flag; rank `dst` waits for the flag
@@ -237,26 +241,45 @@ class PeerGatherer:
         self.layout, self.slot_bytes = layout, off
         flag_bytes = 256
         total = self.SLOTS * self.slot_bytes + flag_bytes
+        # Every rank reaches the same verdict: a rank whose allocation / mapping failed reports it through the (host-side) object
+        # exchange and ALL ranks raise PeerSetupError together, before any device-side flag is waited on -- the caller can then
+        # fall back to OutputGatherer collectively instead of leaving the healthy ranks polling a flag nobody will raise.
         with torch.cuda.device(self.device):
             ptr = C.c_void_p()
             handle = C.create_string_buffer(64)
-            capi.check(L.moge_peer_alloc(total, C.byref(ptr), handle))
-            self.stage = ptr.value
-            self.flag_base = self.stage + self.SLOTS * self.slot_bytes        # int32 flags: [ready[s] for s] then [consumed[s] for s]
+            err = None
+            try:
+                capi.check(L.moge_peer_alloc(total, C.byref(ptr), handle))
+                self.stage = ptr.value
+                self.flag_base = self.stage + self.SLOTS * self.slot_bytes    # int32 flags: [ready[s] for s] then [consumed[s] for s]
+            except Exception as ex:                                            # noqa: BLE001 -- reported to every rank below
+                err = f"rank {self.rank}: {ex}"
             gathered = [None] * self.world
-            dist.all_gather_object(gathered, (self.rank, bytes(handle.raw), total), group=self.group)
-            if self.rank == self.dst:
-                for r, h, tot in gathered:
-                    if r == self.dst or not self.counts[r]:
-                        continue
-                    p = C.c_void_p()
-                    capi.check(L.moge_peer_open(h, C.byref(p)))
-                    self.peers[r] = p.value
-            else:
-                h = [g for g in gathered if g[0] == self.dst][0][1]
-                p = C.c_void_p()
-                capi.check(L.moge_peer_open(h, C.byref(p)))
-                self.flags_dst = p.value + self.SLOTS * self.slot_bytes
+            dist.all_gather_object(gathered, (self.rank, bytes(handle.raw), total, err), group=self.group)
+            errs = [g[3] for g in gathered if g[3]]
+            if not errs:
+                try:
+                    if self.rank == self.dst:
+                        for r, h, tot, _ in gathered:
+                            if r == self.dst or not self.counts[r]:
+                                continue
+                            p = C.c_void_p()
+                            capi.check(L.moge_peer_open(h, C.byref(p)))
+                            self.peers[r] = p.value
+                    else:
+                        h = [g for g in gathered if g[0] == self.dst][0][1]
+                        p = C.c_void_p()
+                        capi.check(L.moge_peer_open(h, C.byref(p)))
+                        self.flags_dst = p.value + self.SLOTS * self.slot_bytes
+                except Exception as ex:                                        # noqa: BLE001
+                    err = f"rank {self.rank}: {ex}"
+                opened = [None] * self.world
+                dist.all_gather_object(opened, err, group=self.group)
+                errs = [e for e in opened if e]
+            if errs:
+                self.close()
+                self.layout = None
+                raise PeerSetupError("peer-memory gather unavailable: " + "; ".join(errs))
         dist.barrier(group=self.group)
 
     def _ready_flag(self, base, slot):
