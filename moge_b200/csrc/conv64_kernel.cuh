@@ -22,7 +22,7 @@ __device__ unsigned long long mg_c64_dbg[8];
 #define C64_ACC(var)
 #endif
 
-template <int BN> struct Conv64Cfg {
+template <int BN, int MW = 1> struct Conv64Cfg {
     static constexpr int kABytes = 160 * 128;                       // box {64 ch, 16 px, 10 rows}
     static constexpr int kWBytes = BN * 128 * 10;                   // 9 taps + 1 aux block, each [BN][64] 128B-swizzled
 #ifndef MG_C64_GROUPS
@@ -34,7 +34,20 @@ template <int BN> struct Conv64Cfg {
     // tiles round-robin, concurrently, so the per-tile epilogue latency chain (TMEM load -> transpose -> global) overlaps.
     static constexpr int kAccStages = 2 * kEpiGroups;
     static constexpr int kEpiWarps = 4 * kEpiGroups;
-    static constexpr int kThreads = 64 + 32 * kEpiWarps;
+    // MW = MMA-issuing warps.  With K = 64 per tap an N = 64 MMA lasts ~48 cycles and a stage is only 12 of them: the issuing
+    // warp's own per-stage work (barrier wait, elect, ~60 uniform-datapath instructions of descriptor arithmetic, commits; ncu
+    // source page: the warp is blocked on a full tensor queue for only 24 % of its samples) is longer than the MMAs it feeds.
+    // With MW = 2 the two issuing warps take alternate tiles (separate accumulator stages), so one warp's bookkeeping runs under
+    // the other's MMAs.  Same-box A/B, B = 32 ViT-L: level-3 res_a 0.637 -> 0.560 ms, res_b 0.691 -> 0.645, the N = 16 / 32 output
+    // convs 1.18 -> 0.89 ms; launches with the extra 1x1 aux stage (4 stages per tile on rings of 3 + 2 slots) lose 4 % and
+    // keep MW = 1 (launch_conv64 picks per launch).
+    static constexpr int kMmaWarps = MW;
+    // two issuing warps: the halo ring is split into one ring per warp (slots [0, kRing0) and [kRing0, kStages)), so that every
+    // full / empty barrier is waited on by exactly one consumer and the phase-parity bookkeeping stays valid
+    static constexpr int kRing0 = (kMmaWarps > 1) ? (kStages + 1) / 2 : kStages;
+    static constexpr int kFirstEpiWarp = 1 + kMmaWarps;
+    static constexpr int kThreads = 32 * (1 + kMmaWarps + kEpiWarps);
+    static_assert(kMmaWarps == 1 || (kMmaWarps == 2 && kAccStages % 2 == 0), "conv64_kernel: 1 or 2 MMA warps (tiles alternate; accumulator stages must split evenly)");
     static constexpr int kTmemCols = (kAccStages * BN <= 32) ? 32 : (kAccStages * BN <= 64) ? 64 : (kAccStages * BN <= 128) ? 128 : (kAccStages * BN <= 256) ? 256 : 512;
     static constexpr int kScratchBytes = kEpiWarps * 4096;
     static constexpr int kSmemBytes = kStages * kABytes + kWBytes + 1024 + 256 + kScratchBytes;
@@ -44,12 +57,12 @@ template <int BN> struct Conv64Cfg {
     static_assert(kAccStages * BN <= 512, "conv64_kernel: accumulator stages exceed tensor memory");
 };
 
-template <int BN, int EPI, bool BF16, int DF>
-__global__ void __launch_bounds__(Conv64Cfg<BN>::kThreads, 1)
+template <int BN, int EPI, bool BF16, int DF, int MMAW>
+__global__ void __launch_bounds__(Conv64Cfg<BN, MMAW>::kThreads, 1)
 conv64_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapAux,
               const __grid_constant__ CUtensorMap mapW, const UmmaParams p) {
     pdl_launch_dependents();      // (the wait sits after the barrier / TMEM set-up below: that prologue overlaps the previous kernel's tail)
-    using Cfg = Conv64Cfg<BN>;
+    using Cfg = Conv64Cfg<BN, MMAW>;
     constexpr int S = Cfg::kStages;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -99,44 +112,54 @@ conv64_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
                 for (int t = 0; t < nblk; ++t) tma_load_2d(sW + t * BN * 128, &mapW, wfull, t * TILE_K, nt * BN);
             }
             __syncwarp();
-            int s = 0; uint32_t ph = 0;
+            int s0 = 0, s1 = 0; uint32_t ph0 = 0, ph1 = 0;    // ring positions (ring 1 only with two issuing warps)
+            int it = 0;
             const int per_img = p.tiles_x * p.tiles_y;
-            for (int mt = mt0; mt < p.num_m_tiles; mt += mstep) {
+            for (int mt = mt0; mt < p.num_m_tiles; mt += mstep, ++it) {
                 const int b = mt / per_img, r = mt % per_img;
                 const int y0 = (r / p.tiles_x) * TILE_PH, x0 = (r % p.tiles_x) * TILE_PW;
+                const bool ring1 = Cfg::kMmaWarps > 1 && (it & 1);
+                const int rbase = ring1 ? Cfg::kRing0 : 0, rdepth = ring1 ? S - Cfg::kRing0 : Cfg::kRing0;
+                int s = ring1 ? s1 : s0; uint32_t ph = ring1 ? ph1 : ph0;
                 for (int i = 0; i < nstage; ++i) {
-                    { C64_T0(); mbar_wait(&empty[s], ph ^ 1); C64_ACC(dbg_a); }
-                    uint8_t* sa = smem + s * Cfg::kABytes;
+                    const int slot = rbase + s;
+                    { C64_T0(); mbar_wait(&empty[slot], ph ^ 1); C64_ACC(dbg_a); }
+                    uint8_t* sa = smem + slot * Cfg::kABytes;
                     if (elect_one()) {
                         if (i < 3) {
-                            mbar_arrive_expect_tx(&full[s], Cfg::kABytes);
-                            tma_load_4d(sa, &mapA, &full[s], 0, x0 + i, y0, b);          // padded rows y0..y0+9 = taps dy 0..2
+                            mbar_arrive_expect_tx(&full[slot], Cfg::kABytes);
+                            tma_load_4d(sa, &mapA, &full[slot], 0, x0 + i, y0, b);          // padded rows y0..y0+9 = taps dy 0..2
                         } else {
-                            mbar_arrive_expect_tx(&full[s], TILE_M * 128);
-                            tma_load_4d(sa, &mapAux, &full[s], 0, x0 + 1, y0 + 1, b);
+                            mbar_arrive_expect_tx(&full[slot], TILE_M * 128);
+                            tma_load_4d(sa, &mapAux, &full[slot], 0, x0 + 1, y0 + 1, b);
                         }
                     }
                     __syncwarp();
-                    if (++s == S) { s = 0; ph ^= 1; }
+                    if (++s == rdepth) { s = 0; ph ^= 1; }
                 }
+                if (ring1) { s1 = s; ph1 = ph; } else { s0 = s; ph0 = ph; }
             }
         }
-    } else if (warp == 1) {
+    } else if (warp <= Cfg::kMmaWarps) {
         {
             constexpr uint32_t idesc = make_idesc(TILE_M, BN, BF16 ? 1u : 0u);
+            constexpr int MW = Cfg::kMmaWarps;
+            const int mw = warp - 1;                   // this warp issues the MMAs of tiles mw, mw + MW, ... of the CTA
             mbar_wait(wfull, 0);
-            int s = 0; uint32_t ph = 0;
-            int it = 0;
             const uint32_t w0 = smem_u32(sW);
-            for (int mt = mt0; mt < p.num_m_tiles; mt += mstep, ++it) {
+            const int rbase = mw ? Cfg::kRing0 : 0, rdepth = mw ? S - Cfg::kRing0 : Cfg::kRing0;      // this warp's halo ring
+            int s = 0; uint32_t ph = 0;
+            int it = mw;
+            for (int mt = mt0 + mw * mstep; mt < p.num_m_tiles; mt += MW * mstep, it += MW) {
                 const int acc = it % Cfg::kAccStages;
                 { C64_T0(); mbar_wait(&tempty[acc], ((it / Cfg::kAccStages) & 1) ^ 1); C64_ACC(dbg_b); }
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * BN;
                 for (int i = 0; i < nstage; ++i) {
-                    { C64_T0(); mbar_wait(&full[s], ph); C64_ACC(dbg_a); }
+                    const int slot = rbase + s;
+                    { C64_T0(); mbar_wait(&full[slot], ph); C64_ACC(dbg_a); }
                     tc_fence_after();
-                    const uint32_t sa = smem_u32(smem + s * Cfg::kABytes);
+                    const uint32_t sa = smem_u32(smem + slot * Cfg::kABytes);
                     if (elect_one()) {
                         if (i < 3) {
 #pragma unroll
@@ -152,16 +175,16 @@ conv64_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
 #pragma unroll
                             for (int k = 0; k < TILE_K / 16; ++k) umma_f16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, 1);
                         }
-                        umma_commit(&empty[s]);
+                        umma_commit(&empty[slot]);
                         if (i == nstage - 1) umma_commit(&tfull[acc]);
                     }
                     __syncwarp();
-                    if (++s == S) { s = 0; ph ^= 1; }
+                    if (++s == rdepth) { s = 0; ph ^= 1; }
                 }
             }
         }
     } else {
-        const int ew = warp - 2;
+        const int ew = warp - Cfg::kFirstEpiWarp;
         const int quarter = warp & 3;
         const int group = ew >> 2;                     // epilogue group g drains tiles g, g + G, ...
         float4* scr = reinterpret_cast<float4*>(scratch_base + ew * 1024);
@@ -183,7 +206,7 @@ conv64_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
     if (lane == 0) {
         if (warp == 0) { atomicAdd(&mg_c64_dbg[0], (unsigned long long)dbg_a); atomicAdd(&mg_c64_dbg[5], (unsigned long long)(clock64() - dbg_start)); }
         if (warp == 1) { atomicAdd(&mg_c64_dbg[1], (unsigned long long)dbg_a); atomicAdd(&mg_c64_dbg[2], (unsigned long long)dbg_b); }
-        if (warp == 2) { atomicAdd(&mg_c64_dbg[3], (unsigned long long)dbg_a); atomicAdd(&mg_c64_dbg[4], (unsigned long long)dbg_b); }
+        if (warp == Cfg::kFirstEpiWarp) { atomicAdd(&mg_c64_dbg[3], (unsigned long long)dbg_a); atomicAdd(&mg_c64_dbg[4], (unsigned long long)dbg_b); }
     }
 #endif
     tc_fence_before();

@@ -18,13 +18,24 @@ namespace mg {
 template <int BN> struct ConvhCfg {
     static constexpr int kABytes = 160 * 128;                       // box {64 ch, 16 px, 10 rows}
     static constexpr int kWBytes = BN * 128;                        // [BN][64] 128B-swizzled
+    // Weight blocks per ring stage.  With one block per stage the MMA warp goes through a barrier wait, an elect, the descriptor
+    // arithmetic and a commit for every FOUR MMAs; at BN = 128 those last 256 tensor cycles while the loop iteration takes ~530
+    // (ncu source page of convh_kernel<128>: the issuing warp never finds the tensor queue full, tensor pipe 50 % active).  Grouping
+    // the three vertical taps of one (channel block, horizontal tap) into one stage gives 12 MMAs per iteration.  The ring holds
+    // the same bytes (2 x 3 blocks instead of 6 x 1); BN = 256 stages would not fit three blocks and are less overhead-bound.
+    // Same-box A/B, B = 32 ViT-L: level-2 res_a 0.531 -> 0.465 ms, res_b 0.561 -> 0.510 ms.
+#ifndef MG_CONVH_WGROUP
+#define MG_CONVH_WGROUP 3      // 1 = one weight block per stage (A/B builds)
+#endif
+    static constexpr int kWGroup = (MG_CONVH_WGROUP == 3 && BN < 256) ? 3 : 1;
+    static constexpr int kWStageBytes = kWGroup * kWBytes;
     static constexpr int kAStages = (BN >= 256) ? 3 : 4;
-    static constexpr int kWStages = (BN >= 256) ? 4 : 6;
+    static constexpr int kWStages = (BN >= 256) ? 4 : (kWGroup == 3 ? 2 : 6);
     static constexpr int kEpiWarps = 8;
     static constexpr int kThreads = 64 + 32 * kEpiWarps;
     static constexpr int kTmemCols = (2 * BN <= 256) ? 256 : 512;
     static constexpr int kScratchBytes = kEpiWarps * 4096;
-    static constexpr int kSmemBytes = kAStages * kABytes + kWStages * kWBytes + 1024 + 256 + kScratchBytes;
+    static constexpr int kSmemBytes = kAStages * kABytes + kWStages * kWStageBytes + 1024 + 256 + kScratchBytes;
     static constexpr int kColsPerWarp = BN / 2;
     static_assert(kSmemBytes <= kMaxDynSmem, "convh_kernel: box ring + weight ring + scratch exceed the shared memory of one CTA");
     static_assert((2 * kAStages + 2 * kWStages + 4) * 8 + 4 <= 256, "convh_kernel: barrier block overflows its 256 bytes");
@@ -41,14 +52,14 @@ convh_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint8_t* sA = smem;
     uint8_t* sW = smem + SA * Cfg::kABytes;
-    uint64_t* full_a = reinterpret_cast<uint64_t*>(sW + SW * Cfg::kWBytes);
+    uint64_t* full_a = reinterpret_cast<uint64_t*>(sW + SW * Cfg::kWStageBytes);
     uint64_t* empty_a = full_a + SA;
     uint64_t* full_w = empty_a + SA;
     uint64_t* empty_w = full_w + SW;
     uint64_t* tfull = empty_w + SW;
     uint64_t* tempty = tfull + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
-    float* scratch_base = reinterpret_cast<float*>(sW + SW * Cfg::kWBytes + 256);
+    float* scratch_base = reinterpret_cast<float*>(sW + SW * Cfg::kWStageBytes + 256);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int total_tiles = p.num_m_tiles * p.num_n_tiles;
@@ -96,6 +107,18 @@ convh_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
                     __syncwarp();
                     if (++sa == SA) { sa = 0; pha ^= 1; }
                     const int nw = aux ? 1 : 3;
+                    if (Cfg::kWGroup == 3) {         // one stage = the (up to) three vertical-tap blocks of this box
+                        mbar_wait(&empty_w[sw], phw ^ 1);
+                        if (elect_one()) {
+                            mbar_arrive_expect_tx(&full_w[sw], nw * Cfg::kWBytes);
+                            for (int dy = 0; dy < nw; ++dy) {
+                                const int kblk = aux ? 9 * kbm + (c - kbm) : (dy * 3 + i) * kbm + c;
+                                tma_load_2d(sW + sw * Cfg::kWStageBytes + dy * Cfg::kWBytes, &mapW, &full_w[sw], kblk * TILE_K, nt * BN);
+                            }
+                        }
+                        __syncwarp();
+                        if (++sw == SW) { sw = 0; phw ^= 1; }
+                    } else
                     for (int dy = 0; dy < nw; ++dy) {
                         mbar_wait(&empty_w[sw], phw ^ 1);
                         if (elect_one()) {
@@ -128,6 +151,33 @@ convh_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
                     tc_fence_after();
                     const uint32_t a0 = smem_u32(sA + sa * Cfg::kABytes);
                     const int nw = aux ? 1 : 3;
+                    if (Cfg::kWGroup == 3) {
+                        mbar_wait(&full_w[sw], phw);
+                        tc_fence_after();
+                        if (elect_one()) {
+                            const uint32_t wbase = smem_u32(sW + sw * Cfg::kWStageBytes);
+                            if (!aux) {
+#pragma unroll
+                                for (int dy = 0; dy < 3; ++dy) {
+                                    const uint64_t adesc = make_sdesc_sw128(a0 + dy * TILE_PW * 128);
+                                    const uint64_t bdesc = make_sdesc_sw128(wbase + dy * Cfg::kWBytes);
+#pragma unroll
+                                    for (int k = 0; k < TILE_K / 16; ++k) umma_f16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, first | dy | k);
+                                }
+                            } else {
+                                const uint64_t adesc = make_sdesc_sw128(a0);
+                                const uint64_t bdesc = make_sdesc_sw128(wbase);
+#pragma unroll
+                                for (int k = 0; k < TILE_K / 16; ++k) umma_f16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, first | k);
+                            }
+                            umma_commit(&empty_w[sw]);
+                            umma_commit(&empty_a[sa]);
+                            if (c == kbm + kba - 1 && i == ni - 1) umma_commit(&tfull[acc]);
+                        }
+                        __syncwarp();
+                        first = 1;
+                        if (++sw == SW) { sw = 0; phw ^= 1; }
+                    } else
                     for (int dy = 0; dy < nw; ++dy) {
                         mbar_wait(&full_w[sw], phw);
                         tc_fence_after();
