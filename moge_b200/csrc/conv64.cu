@@ -8,6 +8,7 @@ namespace mg {
 template <int BN, int EPI, bool BF16, int DF, int MW>
 static int launch_inst(const CUtensorMap& a, const CUtensorMap& aux, const CUtensorMap& w, const UmmaParams& p, int num_sms, cudaStream_t st) {
     using Cfg = Conv64Cfg<BN, MW>;
+    if (MW == 2 && p.kb_aux != 0) return set_error("conv64: the two-issuer form has no aux stage");
     auto kern = conv64_kernel<BN, EPI, BF16, DF, MW>;
     MG_SET_SMEM_ONCE(kern, Cfg::kSmemBytes);
     const int nnt = p.num_n_tiles;

@@ -24,12 +24,18 @@ __device__ unsigned long long mg_c64_dbg[8];
 
 template <int BN, int MW = 1> struct Conv64Cfg {
     static constexpr int kABytes = 160 * 128;                       // box {64 ch, 16 px, 10 rows}
-    static constexpr int kWBytes = BN * 128 * 10;                   // 9 taps + 1 aux block, each [BN][64] 128B-swizzled
+    // resident weights: 9 taps + 1 aux block, each [BN][64] 128B-swizzled.  The two-issuer form never runs aux launches
+    // (launch_conv64), so it keeps 9 blocks and spends the 8 KB on a sixth halo slot: two rings of three slots = one whole tile each
+#ifndef MG_C64_MW2_STAGES
+#define MG_C64_MW2_STAGES 6
+#endif
+    static constexpr int kWBlocks = (MW == 2) ? 9 : 10;
+    static constexpr int kWBytes = BN * 128 * kWBlocks;
 #ifndef MG_C64_GROUPS
 #define MG_C64_GROUPS 2
 #endif
     static constexpr int kEpiGroups = MG_C64_GROUPS;
-    static constexpr int kStages = (BN >= 64) ? (kEpiGroups > 2 ? 4 : 5) : 6;
+    static constexpr int kStages = (BN >= 64) ? (kEpiGroups > 2 ? 4 : (MW == 2 ? MG_C64_MW2_STAGES : 5)) : 6;
     // 2 TMEM accumulator stages per epilogue group; the epilogue warps form kEpiGroups groups of 4 (one warp per TMEM lane quarter) that drain
     // tiles round-robin, concurrently, so the per-tile epilogue latency chain (TMEM load -> transpose -> global) overlaps.
     static constexpr int kAccStages = 2 * kEpiGroups;
@@ -106,7 +112,7 @@ conv64_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
         // assume an arbitrary active mask and wraps every TMA / tcgen05 instruction in an elect-and-retry loop (~9
         // dependent instructions per MMA -- more than a 48-cycle N = 64 MMA takes to execute).
         {
-            const int nblk = 9 + p.kb_aux;
+            const int nblk = (Cfg::kWBlocks == 9) ? 9 : 9 + p.kb_aux;
             if (elect_one()) {
                 mbar_arrive_expect_tx(wfull, nblk * BN * 128);
                 for (int t = 0; t < nblk; ++t) tma_load_2d(sW + t * BN * 128, &mapW, wfull, t * TILE_K, nt * BN);
