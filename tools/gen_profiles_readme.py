@@ -18,7 +18,7 @@ numbers are quoted with their box, every comparison in DESIGN.md is a same-box A
 
 | file | what |
 |---|---|
-| `r2_bench_n1.json` | `python bench.py --steps 10 --warmup 3`, final build: **{b1['value']:.0f} images/s** device-resident ({b1['ms_per_step']:.1f} ms/step), **e2e {b1['e2e']['value']:.0f} images/s** through `serving.InferPipeline` (pinned-host in/out every step; {b1['e2e']['serial']['value']:.0f} with the one-stream serial loop), batch-1 p50 {b1['latency']['p50_ms']:.2f} ms / p90 {b1['latency']['p90_ms']:.2f} ms over 200 runs; SM clock {b1['clocks']['sm_mhz']:.0f} MHz median (`sw_power_cap`); `cpu_baseline` {b1['cpu_baseline']['value']:.2f} images/s on {b1['cpu_baseline']['cores']} cores (12 images); `gpu_baseline` (same-box PyTorch-CUDA comparator, the reference's algorithm as plain torch ops): `.half()` {gb['half']['images_per_s']:.0f} images/s at B=32, batch-1 p50 {gb['half']['batch1_p50_ms']:.1f} ms; fp32 + autocast {gb['autocast']['images_per_s']:.0f} images/s, {gb['autocast']['batch1_p50_ms']:.1f} ms |
+| `r2_bench_n1.json` | `python bench.py --steps 10 --warmup 3`, final build: **{b1['value']:.0f} images/s** device-resident ({b1['ms_per_step']:.1f} ms/step), **e2e {b1['e2e']['value']:.0f} images/s** through `serving.InferPipeline` (pinned-host in/out every step; {b1['e2e']['serial']['value']:.0f} with the one-stream serial loop), batch-1 p50 {b1['latency']['p50_ms']:.2f} ms / p90 {b1['latency']['p90_ms']:.2f} ms over 200 runs; SM clock {b1['clocks']['sm_mhz']:.0f} MHz median (`sw_power_cap`) — a slow-clock box: `r2_bench_n1_prev_build.json` is the previous build (five halo slots in `conv64_kernel`) on a {L('r2_bench_n1_prev_build.json')['clocks']['sm_mhz']:.0f} MHz box: {L('r2_bench_n1_prev_build.json')['value']:.0f} images/s, decoder {L('r2_bench_n1_prev_build.json')['roofline_decoder']['ms_per_step']:.1f} ms; same-box A/B final vs previous build: decoder 14.36 -> 13.47 ms per step; `cpu_baseline` {b1['cpu_baseline']['value']:.2f} images/s on {b1['cpu_baseline']['cores']} cores (12 images); `gpu_baseline` (same-box PyTorch-CUDA comparator, the reference's algorithm as plain torch ops): `.half()` {gb['half']['images_per_s']:.0f} images/s at B=32, batch-1 p50 {gb['half']['batch1_p50_ms']:.1f} ms; fp32 + autocast {gb['autocast']['images_per_s']:.0f} images/s, {gb['autocast']['batch1_p50_ms']:.1f} ms |
 | `r2_bench_reference_arm.json` | `python bench.py --impl reference`: the reference algorithm (oracle port, fp32) on the host cores: {ref['value']:.2f} images/s |
 | `r2_bench_n2.json`, `r2_bench_n8.json` | (taken before the last decoder change, i.e. on a build ≈ 1 ms per step slower; an 8-GPU box for a re-run was not available) `torchrun --nproc-per-node N bench.py --gpus N` (10 steps), `value` = images/s **with the gather of all outputs to rank 0 inside the timed region** (peer-memory gather, `parallel.PeerGatherer`): N=2 {b2['value']:.0f}, **N=8 {b8['value']:.0f} images/s** ({b8['gather']['ms_per_step_pipelined']:.2f} ms/step vs {b8['gather']['ms_per_step_no_gather']:.2f} without the gather; 1.74 GB to rank 0 per step; serial {b8['gather']['ms_per_step_serial']:.2f}; the grouped NCCL isend/irecv gather for comparison: {b8['gather']['nccl_isend_irecv']['ms_per_step_pipelined']:.2f} pipelined / {b8['gather']['nccl_isend_irecv']['ms_per_step_serial']:.2f} serial); compute-only {b8['value_compute_only']:.0f} images/s. `r2_bench_n2_run2.json`: N=2 again with the driver's `--steps 20 --warmup 5` on another box ({L('r2_bench_n2_run2.json')['value']:.0f} images/s; the gather costs {L('r2_bench_n2_run2.json')['gather']['ms_per_step_pipelined'] - L('r2_bench_n2_run2.json')['gather']['ms_per_step_no_gather']:.1f} ms per step there against {b2['gather']['ms_per_step_pipelined'] - b2['gather']['ms_per_step_no_gather']:.1f} ms on the first box: under the power cap the extra copies cost clock) |
 | `r2_bench_config3.json` | (this and the next two rows: build before the last decoder change) `bench.py --config 3` — BASELINE.json configs[2]: ViT-L-normal **bf16**, 32 images of ~700 tokens in five aspect ratios (grids 19x37, 22x32, 26x26, 32x22, 37x19): ragged packing, ONE engine call: **{c3['ragged']['images_per_s']:.0f} images/s, encoder (linears + attention) {c3['ragged']['encoder']['tflops']:.0f} TFLOP/s = {c3['ragged']['encoder']['frac_of_tensor_peak']:.2f} of the sustained tensor peak** (GEMMs {c3['ragged']['encoder']['gemm_tflops']:.0f}, attention {c3['ragged']['encoder']['attention_tflops']:.0f}); same-shape sub-batches (five calls, what the reference's API allows): {c3['bucketed']['images_per_s']:.0f} images/s, encoder {c3['bucketed']['encoder']['frac_of_tensor_peak']:.2f} |
@@ -28,7 +28,7 @@ numbers are quoted with their box, every comparison in DESIGN.md is a same-box A
 | `r2_launch_list_ncu_summary.txt` | `ncu --metrics gpu__time_duration.sum --clock-control none` launch list of `bench.py --steps 2 --warmup 1` on the DEFAULT product path (LayerNorm fold, neck fold, persistent attention), aggregated per kernel (shares, not absolutes) |
 | `r2_ncu_full_gemm_qkv.txt`, `r2_ncu_full_gemm_proj.txt` | `ncu --set full` of `umma2_kernel` (cta_group::2), one qkv launch and one EPI_RESID launch taken from the REAL launch list (`tools/prof_model.py`): qkv tensor pipe 89 % active |
 | `r2_ncu_full_attention.txt` | `attention_kernel` (persistent, B=32, N=1370, 16 heads): tensor pipe 31 %, XU (MUFU) pipe 49 %, issue 43-45 % |
-| `r2_ncu_full_conv64.txt`, `r2_ncu_full_neckout.txt`, `r2_ncu_full_headout.txt` | `conv64_kernel`: a level-3 3x3 conv (C=64, 296x296, `res_b`; final build with two MMA-issuing warps: DRAM 56 % of peak, traffic = algorithmic), the folded neck output (EPI_NECKOUT, N=32; earlier build) and a folded head output (EPI_HEADOUT, N=16; final build) |
+| `r2_ncu_full_conv64.txt`, `r2_ncu_full_neckout.txt`, `r2_ncu_full_headout.txt` | `conv64_kernel`: a level-3 3x3 conv (C=64, 296x296, `res_b`; two MMA-issuing warps, captured with the five-slot ring: DRAM 56 % of peak, traffic = algorithmic), the folded neck output (EPI_NECKOUT, N=32; earlier build) and a folded head output (EPI_HEADOUT, N=16; final build) |
 | `r2_ncu_full_convh128.txt`, `r2_ncu_full_convh256.txt` | `convh_kernel` (3x3, C_in = 128 / 256: halo boxes + streamed weights): tensor pipe 59 % (final build, three weight blocks per stage; 50 % before) / 82 % |
 | `r2_ncu_full_convT.txt` | ConvTranspose2d-as-GEMM launch (`umma_kernel<256,TILES,EPI_DEC,RAW+SHUFFLE>`) |
 | `r2_ncu_traffic.json` | DRAM bytes (read + write) per launch of the dominant kernel of each class from the captures above, next to the algorithmic bytes of the same launch; `bench.py` copies them into `roofline*.traffic` for this workload |
@@ -49,7 +49,7 @@ Roofline (live, from `r2_bench_n1.json`; peaks = MEASURED_PEAKS.json: 1457.5 TFL
 Round 1 -> round 2 on this workload (driver-measured 595 / 602 images/s at the end of round 1): neck's last level folded through the
 heads (-1.06 ms), persistent ragged attention with 25 % of the exponentials on the FMA pipe (-0.8 ms), predicate-free epilogues for
 interior pixel tiles / full row tiles and GELU without the clamp (fc1 -0.6 ms, decoder -0.5 ms), the proj residual staged by TMA
-(-0.35 ms), two MMA-issuing warps in `conv64_kernel` and three weight blocks per stage in `convh_kernel<128>` (-1.1 ms): 607 -> {b1['value']:.0f} images/s
+(-0.35 ms), two MMA-issuing warps with a six-slot halo ring in `conv64_kernel` and three weight blocks per stage in `convh_kernel<128>` (-2.0 ms in same-box A/Bs): 607 -> {b1['value']:.0f} images/s
 (624-640 before the last change, depending on the box); N=8 with the output gather INSIDE the timed region: 4802 images/s (before the last change).
 
 '''
