@@ -143,9 +143,9 @@ def test_conv3x3_halo_streamed_weights(monkeypatch):
             test_conv3x3_replicate_skip_relu(1, 21, 50, 192, 128, dtype)
 
 
-def test_conv3x3_swapped_operands(monkeypatch):
-    """Experimental convs_kernel (weights on the M side, 16x16 pixels on N = 256), enabled by MOGE_B200_CONVS=1."""
-    monkeypatch.setenv("MOGE_B200_CONVS", "1")
+def test_conv3x3_c64_resident_weights():
+    """conv64_kernel (C_in = 64: resident weights, halo boxes, two MMA-issuing warps on alternate tiles) with one and two
+    output-channel tiles, ragged image edges."""
     for dtype in (torch.float16, torch.bfloat16):
         test_conv3x3_replicate_skip_relu(2, 40, 50, 64, 64, dtype)
         test_conv3x3_replicate_skip_relu(1, 33, 47, 64, 128, dtype)
