@@ -483,7 +483,8 @@ def run_engine(a):
         line["gather"] = gather
         line["value_with_gather"] = line["value"]
         line["config"]["value_definition"] = ("N > 1: images/s from inputs resident on each GPU to ALL outputs resident on rank 0 "
-                                              "(NCCL gather inside the timed region, overlapped with the next step's compute)")
+                                              "(output gather inside the timed region, overlapped with the next step's compute; "
+                                              "transport: see gather.api)")
     sys.stdout.flush()
     os.dup2(saved_stdout, 1)
     print(json.dumps(line), flush=True)
