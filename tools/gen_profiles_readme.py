@@ -20,7 +20,7 @@ numbers are quoted with their box, every comparison in DESIGN.md is a same-box A
 |---|---|
 | `r2_bench_n1.json` | `python bench.py --steps 10 --warmup 3`, final build: **{b1['value']:.0f} images/s** device-resident ({b1['ms_per_step']:.1f} ms/step), **e2e {b1['e2e']['value']:.0f} images/s** through `serving.InferPipeline` (pinned-host in/out every step; {b1['e2e']['serial']['value']:.0f} with the one-stream serial loop), batch-1 p50 {b1['latency']['p50_ms']:.2f} ms / p90 {b1['latency']['p90_ms']:.2f} ms over 200 runs; SM clock {b1['clocks']['sm_mhz']:.0f} MHz median (`sw_power_cap`) — a slow-clock box: `r2_bench_n1_prev_build.json` is the previous build (five halo slots in `conv64_kernel`) on a {L('r2_bench_n1_prev_build.json')['clocks']['sm_mhz']:.0f} MHz box: {L('r2_bench_n1_prev_build.json')['value']:.0f} images/s, decoder {L('r2_bench_n1_prev_build.json')['roofline_decoder']['ms_per_step']:.1f} ms; same-box A/B final vs previous build: decoder 14.36 -> 13.47 ms per step; `cpu_baseline` {b1['cpu_baseline']['value']:.2f} images/s on {b1['cpu_baseline']['cores']} cores (12 images); `gpu_baseline` (same-box PyTorch-CUDA comparator, the reference's algorithm as plain torch ops): `.half()` {gb['half']['images_per_s']:.0f} images/s at B=32, batch-1 p50 {gb['half']['batch1_p50_ms']:.1f} ms; fp32 + autocast {gb['autocast']['images_per_s']:.0f} images/s, {gb['autocast']['batch1_p50_ms']:.1f} ms |
 | `r2_bench_reference_arm.json` | `python bench.py --impl reference`: the reference algorithm (oracle port, fp32) on the host cores: {ref['value']:.2f} images/s |
-| `r2_bench_n2.json`, `r2_bench_n8.json` | (taken before the last decoder change, i.e. on a build ≈ 1 ms per step slower; an 8-GPU box for a re-run was not available) `torchrun --nproc-per-node N bench.py --gpus N` (10 steps), `value` = images/s **with the gather of all outputs to rank 0 inside the timed region** (peer-memory gather, `parallel.PeerGatherer`): N=2 {b2['value']:.0f}, **N=8 {b8['value']:.0f} images/s** ({b8['gather']['ms_per_step_pipelined']:.2f} ms/step vs {b8['gather']['ms_per_step_no_gather']:.2f} without the gather; 1.74 GB to rank 0 per step; serial {b8['gather']['ms_per_step_serial']:.2f}; the grouped NCCL isend/irecv gather for comparison: {b8['gather']['nccl_isend_irecv']['ms_per_step_pipelined']:.2f} pipelined / {b8['gather']['nccl_isend_irecv']['ms_per_step_serial']:.2f} serial); compute-only {b8['value_compute_only']:.0f} images/s. `r2_bench_n2_run2.json`: N=2 again with the driver's `--steps 20 --warmup 5` on another box ({L('r2_bench_n2_run2.json')['value']:.0f} images/s; the gather costs {L('r2_bench_n2_run2.json')['gather']['ms_per_step_pipelined'] - L('r2_bench_n2_run2.json')['gather']['ms_per_step_no_gather']:.1f} ms per step there against {b2['gather']['ms_per_step_pipelined'] - b2['gather']['ms_per_step_no_gather']:.1f} ms on the first box: under the power cap the extra copies cost clock) |
+| `r2_bench_n2.json`, `r2_bench_n8.json` | (taken before the last decoder change, i.e. on a build ≈ 1 ms per step slower; an 8-GPU box for a re-run was not available) `torchrun --nproc-per-node N bench.py --gpus N` (10 steps), `value` = images/s **with the gather of all outputs to rank 0 inside the timed region** (peer-memory gather, `parallel.PeerGatherer`): N=2 {b2['value']:.0f}, **N=8 {b8['value']:.0f} images/s** ({b8['gather']['ms_per_step_pipelined']:.2f} ms/step vs {b8['gather']['ms_per_step_no_gather']:.2f} without the gather; 1.74 GB to rank 0 per step; serial {b8['gather']['ms_per_step_serial']:.2f}; the grouped NCCL isend/irecv gather for comparison: {b8['gather']['nccl_isend_irecv']['ms_per_step_pipelined']:.2f} pipelined / {b8['gather']['nccl_isend_irecv']['ms_per_step_serial']:.2f} serial); compute-only {b8['value_compute_only']:.0f} images/s. `r2_bench_n2_run2.json`: N=2 again with the driver's `--steps 20 --warmup 5` on another box ({L('r2_bench_n2_run2.json')['value']:.0f} images/s; the gather costs {L('r2_bench_n2_run2.json')['gather']['ms_per_step_pipelined'] - L('r2_bench_n2_run2.json')['gather']['ms_per_step_no_gather']:.1f} ms per step there against {b2['gather']['ms_per_step_pipelined'] - b2['gather']['ms_per_step_no_gather']:.1f} ms on the first box; the difference between the boxes was not isolated) |
 | `r2_bench_config3.json` | (this and the next two rows: build before the last decoder change) `bench.py --config 3` — BASELINE.json configs[2]: ViT-L-normal **bf16**, 32 images of ~700 tokens in five aspect ratios (grids 19x37, 22x32, 26x26, 32x22, 37x19): ragged packing, ONE engine call: **{c3['ragged']['images_per_s']:.0f} images/s, encoder (linears + attention) {c3['ragged']['encoder']['tflops']:.0f} TFLOP/s = {c3['ragged']['encoder']['frac_of_tensor_peak']:.2f} of the sustained tensor peak** (GEMMs {c3['ragged']['encoder']['gemm_tflops']:.0f}, attention {c3['ragged']['encoder']['attention_tflops']:.0f}); same-shape sub-batches (five calls, what the reference's API allows): {c3['bucketed']['images_per_s']:.0f} images/s, encoder {c3['bucketed']['encoder']['frac_of_tensor_peak']:.2f} |
 | `r2_bench_config5.json` | `bench.py --config 5` — configs[4]: ViT-B (SURVEY.md 8 test config), B=8, long side {{256,384,518,768,1024}} x aspect {{2:1,3:2,1:1,2:3,1:2}} x resolution_level {{0,5,9}}: 75 rows each with (HxW, T_req -> grid, images/s, decoder ms, decoder fraction of the HBM bound by SURVEY 8(d)'s bytes, encoder fraction); whole sweep {c5['value']:.0f} images/s, decoder {c5['roofline']['frac']:.2f} of the HBM peak |
 | `r2_bench_n1_tokens3600_batch8.json` | `infer()` default token count (3600 -> 60x60 grid), 8 images/step: {t36['value']:.0f} images/s, batch-1 p50 {t36['latency']['p50_ms']:.2f} ms; encoder GEMMs {t36['roofline']['frac']:.2f}, attention {t36['roofline_attention']['frac']:.2f}, decoder {t36['roofline_decoder']['frac']:.2f} |
