@@ -34,6 +34,7 @@ numbers are quoted with their box, every comparison in DESIGN.md is a same-box A
 | `r2_ncu_traffic.json` | DRAM bytes (read + write) per launch of the dominant kernel of each class from the captures above, next to the algorithmic bytes of the same launch; `bench.py` copies them into `roofline*.traffic` for this workload |
 | `r2_gpu_baseline_kernels.json` | `torch.profiler` kernel list of one batch-1 pass of the PyTorch-CUDA comparator (`.half()` mode): 864 launches — cuBLAS `nvjet` GEMMs, cuDNN implicit-GEMM convs with NCHW<->NHWC transposes, cuDNN flash SDPA, elementwise / pad / upsample kernels, 2 D2H copies for the host SciPy solve |
 | `r2_error_attribution.json` | `tools/error_attribution.py`: engine vs fp32 oracle on the benchmarked shape, the F.normalize amplification of the raw normal error, and the 16-bit rounding-site sensitivity table quoted in DESIGN.md section 2 |
+| `r2_sass_summary.txt` | `tools/sass_summary.py`: tcgen05 / TMA / tensor-memory instruction counts per kernel family in the shipped `libmoge_b200.so` (final build) |
 | `r2_pipe_rates.txt` | `tools/pipe_rates.cu`: measured cycles per warp-instruction per scheduler of the instructions the attention softmax is made of |
 | `r2_sanitizer_memcheck_ops.log`, `r2_sanitizer_memcheck_model_final.log`, `r2_sanitizer_memcheck_model.log` | `compute-sanitizer --tool memcheck`, 0 errors: the op-level + geometry tests (68) and three model tests (batch chunking, neck fold, mixed-shape `infer_many`) on the FINAL build; the 14-test model subset on the build before the decoder issue-side changes |
 | `r1_*` | round-1 files, kept for the record (earlier kernels; `r1_launch_list_ncu_summary.txt` was taken with `MOGE_B200_LNFOLD=0`) |
